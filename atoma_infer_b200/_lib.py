@@ -1,0 +1,183 @@
+"""ctypes binding of libflashattention.so (include/atoma_flash.h + include/atoma_ops.h).
+
+The library is the product; this module only loads it and declares signatures.  There is no
+fallback: if the shared library is missing the import fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("ATOMA_FLASH_LIB", _PKG / "lib" / "libflashattention.so"))
+
+MAX_RANK = 5
+DEVICE_CPU = -1
+F16, BF16, F32, U32, I64, U8, F64 = range(7)
+
+
+class Tensor(C.Structure):
+    """struct atoma_tensor"""
+
+    _fields_ = [
+        ("data", C.c_void_p),
+        ("dtype", C.c_int32),
+        ("device", C.c_int32),
+        ("rank", C.c_int32),
+        ("shape", C.c_int64 * MAX_RANK),
+        ("stride", C.c_int64 * MAX_RANK),
+    ]
+
+
+class MhaArgs(C.Structure):
+    """struct atoma_mha_args — the run_mha argument tuple (reference csrc/src/ffi.rs:4-66)."""
+
+    _fields_ = [
+        ("q_ptr", C.c_void_p), ("k_ptr", C.c_void_p), ("v_ptr", C.c_void_p), ("o_ptr", C.c_void_p),
+        ("softmax_lse_ptr", C.c_void_p), ("alibi_slopes_ptr", C.c_void_p),
+        ("cu_seqlens_q_ptr", C.c_void_p), ("cu_seqlens_k_ptr", C.c_void_p),
+        ("is_seqlens_k_cumulative", C.c_bool),
+        ("q_batch_stride", C.c_uint32), ("k_batch_stride", C.c_uint32),
+        ("v_batch_stride", C.c_uint32), ("o_batch_stride", C.c_uint32),
+        ("alibi_slopes_batch_stride", C.c_uint32),
+        ("q_row_stride", C.c_uint32), ("k_row_stride", C.c_uint32),
+        ("v_row_stride", C.c_uint32), ("o_row_stride", C.c_uint32),
+        ("q_head_stride", C.c_uint32), ("k_head_stride", C.c_uint32),
+        ("v_head_stride", C.c_uint32), ("o_head_stride", C.c_uint32),
+        ("num_splits", C.c_uint32),
+        ("b", C.c_uint32), ("h", C.c_uint32), ("h_k", C.c_uint32), ("d", C.c_uint32),
+        ("d_rounded", C.c_uint32),
+        ("softmax_scale", C.c_float), ("scale_softmax_log2", C.c_float),
+        ("block_table", C.c_void_p), ("block_table_batch_stride", C.c_uint32),
+        ("page_block_size", C.c_int),
+        ("seqused_k", C.c_void_p),
+        ("seqlen_q", C.c_uint32), ("seqlen_k", C.c_uint32),
+        ("seqlen_q_rounded", C.c_uint32), ("seqlen_k_rounded", C.c_uint32),
+        ("is_bf16", C.c_int), ("is_causal", C.c_int),
+        ("window_size_left", C.c_int), ("window_size_right", C.c_int),
+        ("softcap", C.c_float),
+        ("unpadded_lse", C.c_bool), ("force_split_kernel", C.c_bool),
+        ("softmax_lseaccum_ptr", C.c_void_p), ("oaccum_ptr", C.c_void_p),
+    ]
+
+
+class MhaPlan(C.Structure):
+    """struct atoma_mha_plan"""
+
+    _fields_ = [
+        ("args", MhaArgs),
+        ("out_rank", C.c_int32),
+        ("out_shape", C.c_int64 * 4),
+        ("lse_elems", C.c_int64),
+        ("lseaccum_elems", C.c_int64),
+        ("oaccum_elems", C.c_int64),
+        ("seqlenq_ngroups_swapped", C.c_int32),
+    ]
+
+
+class AttentionConfig(C.Structure):
+    _fields_ = [
+        ("num_heads", C.c_int64), ("num_kv_heads", C.c_int64), ("head_dim", C.c_int64),
+        ("softmax_scale", C.c_float), ("sliding_window", C.c_int64),
+    ]
+
+
+class AttentionMetadata(C.Structure):
+    _fields_ = [
+        ("slot_mapping", C.POINTER(Tensor)),
+        ("num_prefill_tokens", C.c_int64), ("num_decoding_tokens", C.c_int64),
+        ("has_prefill", C.c_int32),
+        ("prefill_block_tables", C.POINTER(Tensor)),
+        ("max_prefill_sequence_length", C.c_int64),
+        ("query_start_locations", C.POINTER(Tensor)),
+        ("sequence_start_locations", C.POINTER(Tensor)),
+        ("max_prefill_sequence_length_k", C.c_int64),
+        ("has_decode", C.c_int32),
+        ("decode_block_tables", C.POINTER(Tensor)),
+        ("decode_sequence_lengths", C.POINTER(Tensor)),
+    ]
+
+
+# Exact C parameter lists, in header order.
+_RUN_MHA_ARGS = [
+    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,  # q k v o lse alibi
+    C.c_void_p, C.c_void_p,  # cu_seqlens_q, cu_seqlens_k
+    C.c_bool,
+    C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,  # batch strides + alibi
+    C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,  # row strides
+    C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,  # head strides
+    C.c_uint32,  # num_splits
+    C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,  # b h h_k d d_rounded
+    C.c_float, C.c_float,
+    C.c_void_p, C.c_uint32, C.c_int,  # block_table, stride, page
+    C.c_void_p,  # seqused_k
+    C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,  # seqlens
+    C.c_int, C.c_int, C.c_int, C.c_int,  # is_bf16 is_causal wl wr
+    C.c_float, C.c_bool, C.c_bool,
+    C.c_void_p, C.c_void_p,
+]
+
+# symbol -> (restype, argtypes); every symbol include/*.h declares is listed here and checked by
+# tests/test_abi.py against the headers.
+SIGNATURES = {
+    # atoma_flash.h, part 1 (reference ABI)
+    "run_mha": (None, _RUN_MHA_ARGS),
+    "copy_blocks_f16": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
+    "copy_blocks_bf16": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
+    "reshape_and_cache_flash": (None, [C.c_void_p] * 5 + [C.c_int64] * 7 + [C.c_uint32, C.c_void_p]),
+    # part 2 (extensions)
+    "run_mha_stream": (None, _RUN_MHA_ARGS + [C.c_void_p]),
+    "swap_blocks_batched": (None, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                   C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
+    "atoma_gemm_bf16_tn": (None, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int64] * 6 + [C.c_void_p]),
+    "atoma_last_status": (C.c_int, []),
+    "atoma_last_error": (C.c_char_p, []),
+    "atoma_last_mha_path": (C.c_char_p, []),
+    "atoma_launch_count": (C.c_int64, []),
+    "atoma_reset_launch_count": (None, []),
+    "atoma_version": (C.c_char_p, []),
+    # atoma_ops.h
+    "atoma_flash_attn_plan": (C.c_char_p, [C.POINTER(Tensor)] * 4 + [C.c_float, C.c_int64, C.c_int64, C.c_float,
+                                                                    C.c_int, C.POINTER(MhaPlan)]),
+    "atoma_flash_attn_varlen_plan": (C.c_char_p, [C.POINTER(Tensor)] * 8 + [C.c_int64, C.c_int64, C.c_float,
+                                                                           C.c_int64, C.c_int64, C.c_float, C.c_int,
+                                                                           C.POINTER(MhaPlan)]),
+    "atoma_flash_attn_kv_cache_plan": (C.c_char_p, [C.POINTER(Tensor)] * 6 + [C.c_float, C.c_int64, C.c_int64,
+                                                                             C.c_int, C.POINTER(MhaPlan)]),
+    "atoma_mha_execute": (C.c_char_p, [C.POINTER(MhaPlan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int, C.c_void_p]),
+    "atoma_compute_num_splits": (C.c_uint32, [C.c_int64] * 5 + [C.c_int]),
+    "atoma_reshape_and_cache_flash": (C.c_char_p, [C.POINTER(Tensor)] * 5 + [C.c_void_p]),
+    "atoma_copy_blocks": (C.c_char_p, [C.POINTER(Tensor), C.c_int64, C.POINTER(Tensor), C.c_int64,
+                                       C.POINTER(Tensor), C.c_void_p, C.c_void_p]),
+    "atoma_swap_blocks": (C.c_char_p, [C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(C.c_int64),
+                                       C.POINTER(C.c_int64), C.c_int64, C.c_void_p]),
+    "atoma_flash_attention_forward": (C.c_char_p, [C.POINTER(AttentionConfig)] + [C.POINTER(Tensor)] * 5 +
+                                      [C.POINTER(AttentionMetadata), C.POINTER(Tensor), C.c_void_p]),
+}
+
+
+def load(path: os.PathLike | str | None = None) -> C.CDLL:
+    p = Path(path) if path else LIB_PATH
+    if not p.exists():
+        raise ImportError(
+            f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"(or `make -C atoma_infer_b200/csrc`). There is no CPU or PyTorch fallback for this library."
+        )
+    lib = C.CDLL(str(p), mode=C.RTLD_LOCAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+_LIB: C.CDLL | None = None
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        _LIB = load()
+    return _LIB

@@ -1,0 +1,391 @@
+// KV-cache maintenance kernels for sm_100a: reshape_and_cache_flash, copy_blocks, swap_blocks.
+//
+// Semantics follow the reference's csrc/kernels/cache_manager.cu (copy_blocks_kernel :16-37,
+// reshape_and_cache_flash_kernel :140-170) and csrc/src/cache_manager.rs:18-128 (swap_blocks);
+// the implementation is new: whole cache blocks move as cp.async.bulk (TMA 1-D) global->shared->
+// global transfers driven by one thread per CTA, token rows move as 16-byte vectors.  All of it is
+// pure data movement, bit-exact by construction.
+#include "atoma_flash.h"
+#include "common.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace atoma {
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Bulk-async block mover
+// ---------------------------------------------------------------------------------------------
+constexpr int kPieceBytes = 16 * 1024;  // one bulk transfer
+constexpr int kRing = 4;                // ring slots per CTA (64 KiB smem -> 3 CTAs / SM)
+
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes,
+                                         uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+// Moves `nspans` spans of `bytes` bytes each (16-byte aligned, bytes % 16 == 0) through a
+// kRing-deep shared-memory ring.  Called by ONE thread of the CTA.
+struct Span {
+    const char *src;
+    char *dst;
+};
+
+template <typename SpanFn>
+__device__ void bulk_move(SpanFn span_of, int nspans, int64_t bytes, char *ring, uint64_t *bars) {
+    const int pieces_per_span = static_cast<int>((bytes + kPieceBytes - 1) / kPieceBytes);
+    const int total = nspans * pieces_per_span;
+    auto piece = [&](int idx, const char *&src, char *&dst, uint32_t &n) {
+        const int s = idx / pieces_per_span, p = idx % pieces_per_span;
+        const Span sp = span_of(s);
+        const int64_t off = static_cast<int64_t>(p) * kPieceBytes;
+        n = static_cast<uint32_t>(min(static_cast<int64_t>(kPieceBytes), bytes - off));
+        src = sp.src + off;
+        dst = sp.dst + off;
+    };
+    auto issue_load = [&](int idx) {
+        const char *src;
+        char *dst;
+        uint32_t n;
+        piece(idx, src, dst, n);
+        const int slot = idx % kRing;
+        mbar_arrive_expect_tx(&bars[slot], n);
+        bulk_g2s(ring + slot * kPieceBytes, src, n, &bars[slot]);
+    };
+    // Loads run kRing-1 pieces ahead of the stores.  Piece i lives in slot i % kRing and completes
+    // phase i / kRing of that slot's mbarrier.
+    for (int i = 0; i < total && i < kRing - 1; ++i) issue_load(i);
+    for (int idx = 0; idx < total; ++idx) {
+        const int ahead = idx + kRing - 1;
+        if (ahead < total) {
+            // `ahead` reuses the slot piece idx-1 was stored from: that store must have finished
+            // READING shared memory (not necessarily writing global memory).
+            if (idx > 0) bulk_wait_read<0>();
+            issue_load(ahead);
+        }
+        const int slot = idx % kRing;
+        mbar_wait(&bars[slot], (idx / kRing) & 1);
+        const char *src;
+        char *dst;
+        uint32_t n;
+        piece(idx, src, dst, n);
+        bulk_s2g(dst, ring + slot * kPieceBytes, n);
+        bulk_commit();
+    }
+    bulk_wait_read<0>();
+}
+
+__global__ void __launch_bounds__(32)
+copy_blocks_bulk_kernel(const int64_t *__restrict__ key_cache_ptrs,
+                        const int64_t *__restrict__ value_cache_ptrs,
+                        const int64_t *__restrict__ block_mapping, int64_t block_bytes) {
+    extern __shared__ __align__(128) char ring[];
+    __shared__ __align__(8) uint64_t bars[kRing];
+    if (threadIdx.x != 0) return;
+    for (int i = 0; i < kRing; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+    const int layer = blockIdx.x;
+    const int64_t pair = blockIdx.y;
+    const int64_t src_block = block_mapping[2 * pair];
+    const int64_t dst_block = block_mapping[2 * pair + 1];
+    char *kbase = reinterpret_cast<char *>(key_cache_ptrs[layer]);
+    char *vbase = reinterpret_cast<char *>(value_cache_ptrs[layer]);
+    auto span_of = [&](int s) {
+        char *base = s == 0 ? kbase : vbase;
+        return Span{base + src_block * block_bytes, base + dst_block * block_bytes};
+    };
+    bulk_move(span_of, 2, block_bytes, ring, bars);
+}
+
+__global__ void __launch_bounds__(32)
+swap_blocks_bulk_kernel(char *__restrict__ dst_base, const char *__restrict__ src_base,
+                        const int64_t *__restrict__ src_blocks,
+                        const int64_t *__restrict__ dst_blocks, int64_t block_bytes) {
+    extern __shared__ __align__(128) char ring[];
+    __shared__ __align__(8) uint64_t bars[kRing];
+    if (threadIdx.x != 0) return;
+    for (int i = 0; i < kRing; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+    const int64_t pair = blockIdx.x;
+    const int64_t sb = src_blocks[pair], db = dst_blocks[pair];
+    auto span_of = [&](int) { return Span{src_base + sb * block_bytes, dst_base + db * block_bytes}; };
+    bulk_move(span_of, 1, block_bytes, ring, bars);
+}
+
+// Fallback for blocks that are not 16-byte aligned / sized: 2-byte elements, same indexing as the
+// reference kernel (cache_manager.cu:31-36).
+__global__ void copy_blocks_scalar_kernel(const int64_t *__restrict__ key_cache_ptrs,
+                                          const int64_t *__restrict__ value_cache_ptrs,
+                                          const int64_t *__restrict__ block_mapping,
+                                          int64_t numel_per_block) {
+    const int layer = blockIdx.x;
+    const int64_t pair = blockIdx.y;
+    uint16_t *kc = reinterpret_cast<uint16_t *>(key_cache_ptrs[layer]);
+    uint16_t *vc = reinterpret_cast<uint16_t *>(value_cache_ptrs[layer]);
+    const int64_t so = block_mapping[2 * pair] * numel_per_block;
+    const int64_t dofs = block_mapping[2 * pair + 1] * numel_per_block;
+    for (int64_t i = threadIdx.x; i < numel_per_block; i += blockDim.x) {
+        kc[dofs + i] = kc[so + i];
+        vc[dofs + i] = vc[so + i];
+    }
+}
+
+__global__ void swap_blocks_scalar_kernel(char *__restrict__ dst_base,
+                                          const char *__restrict__ src_base,
+                                          const int64_t *__restrict__ src_blocks,
+                                          const int64_t *__restrict__ dst_blocks,
+                                          int64_t block_bytes) {
+    const int64_t pair = blockIdx.x;
+    const char *s = src_base + src_blocks[pair] * block_bytes;
+    char *d = dst_base + dst_blocks[pair] * block_bytes;
+    for (int64_t i = threadIdx.x; i < block_bytes; i += blockDim.x) d[i] = s[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// reshape_and_cache_flash
+// ---------------------------------------------------------------------------------------------
+// One "chunk" = 16 bytes of one token's [num_heads*head_size] row.  A thread moves the same chunk
+// of K and of V for kUnroll tokens per iteration (all loads issued before the stores).
+constexpr int kRcThreads = 256;
+constexpr int kRcUnroll = 4;
+
+__global__ void __launch_bounds__(kRcThreads)
+reshape_and_cache_flash_vec_kernel(const char *__restrict__ key, const char *__restrict__ value,
+                                   char *__restrict__ k_cache, char *__restrict__ v_cache,
+                                   const int64_t *__restrict__ slot_mapping, int64_t num_tokens,
+                                   int chunks_per_token, int64_t key_stride_b,
+                                   int64_t value_stride_b, int64_t block_stride_b,
+                                   int64_t row_bytes, int64_t block_size) {
+    const int64_t total = num_tokens * chunks_per_token;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kRcThreads;
+    for (int64_t base = static_cast<int64_t>(blockIdx.x) * kRcThreads + threadIdx.x; base < total;
+         base += stride * kRcUnroll) {
+        uint4 kv[kRcUnroll], vv[kRcUnroll];
+        int64_t dst_off[kRcUnroll];
+#pragma unroll
+        for (int u = 0; u < kRcUnroll; ++u) {
+            const int64_t idx = base + u * stride;
+            dst_off[u] = -1;
+            if (idx < total) {
+                const int64_t token = idx / chunks_per_token;
+                const int chunk = static_cast<int>(idx - token * chunks_per_token);
+                const int64_t slot = slot_mapping[token];
+                if (slot >= 0) {  // slot < 0: padded token, skipped (cache_manager.cu:151-155)
+                    const int64_t blk = slot / block_size, off = slot % block_size;
+                    dst_off[u] = blk * block_stride_b + off * row_bytes + chunk * 16;
+                    kv[u] = ld_nc_v4(key + token * key_stride_b + chunk * 16);
+                    vv[u] = ld_nc_v4(value + token * value_stride_b + chunk * 16);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kRcUnroll; ++u) {
+            if (dst_off[u] >= 0) {
+                *reinterpret_cast<uint4 *>(k_cache + dst_off[u]) = kv[u];
+                *reinterpret_cast<uint4 *>(v_cache + dst_off[u]) = vv[u];
+            }
+        }
+    }
+}
+
+__global__ void reshape_and_cache_flash_scalar_kernel(
+    const uint16_t *__restrict__ key, const uint16_t *__restrict__ value,
+    uint16_t *__restrict__ k_cache, uint16_t *__restrict__ v_cache,
+    const int64_t *__restrict__ slot_mapping, int64_t block_stride, int64_t key_stride,
+    int64_t value_stride, int64_t n, int64_t block_size) {
+    const int64_t token = blockIdx.x;
+    const int64_t slot = slot_mapping[token];
+    if (slot < 0) return;
+    const int64_t blk = slot / block_size, off = slot % block_size;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const int64_t tgt = blk * block_stride + off * n + i;
+        k_cache[tgt] = key[token * key_stride + i];
+        v_cache[tgt] = value[token * value_stride + i];
+    }
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+void copy_blocks_impl(void *key_cache_ptrs, void *value_cache_ptrs, const void *block_mapping,
+                      int64_t num_layers, int64_t num_pairs, int64_t numel_per_block,
+                      cudaStream_t stream) {
+    clear_status();
+    if (num_layers <= 0 || num_pairs <= 0 || numel_per_block <= 0) return;
+    if (num_pairs > 65535) {
+        // gridDim.y limit; issue in slabs.
+        const int64_t *bm = static_cast<const int64_t *>(block_mapping);
+        for (int64_t p0 = 0; p0 < num_pairs; p0 += 65535) {
+            copy_blocks_impl(key_cache_ptrs, value_cache_ptrs, bm + 2 * p0, num_layers,
+                             std::min<int64_t>(65535, num_pairs - p0), numel_per_block, stream);
+        }
+        return;
+    }
+    const int64_t block_bytes = numel_per_block * 2;
+    dim3 grid(static_cast<unsigned>(num_layers), static_cast<unsigned>(num_pairs));
+    // The base pointers live in device memory; blocks of a 16-bit cache allocated by any CUDA
+    // allocator are 256-byte aligned, so 16-byte alignment reduces to block_bytes % 16 == 0.  A
+    // misaligned base would fault the bulk copy loudly rather than corrupt data.
+    if (block_bytes % 16 == 0) {
+        static thread_local int attr_dev = -1;
+        const DeviceInfo &di = current_device_info();
+        if (attr_dev != di.ordinal) {
+            cudaFuncSetAttribute(copy_blocks_bulk_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kRing * kPieceBytes);
+            cudaFuncSetAttribute(swap_blocks_bulk_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kRing * kPieceBytes);
+            attr_dev = di.ordinal;
+        }
+        copy_blocks_bulk_kernel<<<grid, 32, kRing * kPieceBytes, stream>>>(
+            static_cast<const int64_t *>(key_cache_ptrs),
+            static_cast<const int64_t *>(value_cache_ptrs),
+            static_cast<const int64_t *>(block_mapping), block_bytes);
+    } else {
+        const int threads = static_cast<int>(std::min<int64_t>(1024, numel_per_block));
+        copy_blocks_scalar_kernel<<<grid, threads, 0, stream>>>(
+            static_cast<const int64_t *>(key_cache_ptrs),
+            static_cast<const int64_t *>(value_cache_ptrs),
+            static_cast<const int64_t *>(block_mapping), numel_per_block);
+    }
+    note_launch();
+    check_launch("copy_blocks");
+}
+
+}  // namespace
+}  // namespace atoma
+
+using namespace atoma;
+
+extern "C" void copy_blocks_f16(void *key_cache_ptrs, void *value_cache_ptrs,
+                                const void *block_mapping, int64_t num_layers, int64_t num_pairs,
+                                int64_t numel_per_block, atoma_stream_t stream) {
+    copy_blocks_impl(key_cache_ptrs, value_cache_ptrs, block_mapping, num_layers, num_pairs,
+                     numel_per_block, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" void copy_blocks_bf16(void *key_cache_ptrs, void *value_cache_ptrs,
+                                 const void *block_mapping, int64_t num_layers, int64_t num_pairs,
+                                 int64_t numel_per_block, atoma_stream_t stream) {
+    copy_blocks_impl(key_cache_ptrs, value_cache_ptrs, block_mapping, num_layers, num_pairs,
+                     numel_per_block, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" void reshape_and_cache_flash(void *key, void *value, void *key_cache, void *value_cache,
+                                        int64_t *slot_mapping, int64_t block_stride,
+                                        int64_t num_tokens, int64_t num_heads, int64_t head_size,
+                                        int64_t block_size, int64_t key_stride,
+                                        int64_t value_stride, uint32_t dtype,
+                                        atoma_stream_t stream_) {
+    clear_status();
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (dtype > 1) {  // the reference silently does nothing for other dtypes (cache_manager.cu:237-241)
+        set_status(kErrUnsupported, "reshape_and_cache_flash: dtype %u (0 = f16, 1 = bf16)", dtype);
+        return;
+    }
+    if (num_tokens <= 0 || num_heads <= 0 || head_size <= 0) return;
+    const int64_t n = num_heads * head_size;
+    const int64_t row_bytes = n * 2;
+    const bool vec_ok = row_bytes % 16 == 0 && aligned16(key) && aligned16(value) &&
+                        aligned16(key_cache) && aligned16(value_cache) &&
+                        (key_stride * 2) % 16 == 0 && (value_stride * 2) % 16 == 0 &&
+                        (block_stride * 2) % 16 == 0;
+    if (vec_ok) {
+        const int chunks = static_cast<int>(row_bytes / 16);
+        const int64_t total = num_tokens * chunks;
+        const DeviceInfo &di = current_device_info();
+        const int64_t want = (total + kRcThreads * kRcUnroll - 1) / (kRcThreads * kRcUnroll);
+        const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, di.sm_count * 8)));
+        reshape_and_cache_flash_vec_kernel<<<grid, kRcThreads, 0, stream>>>(
+            static_cast<const char *>(key), static_cast<const char *>(value),
+            static_cast<char *>(key_cache), static_cast<char *>(value_cache), slot_mapping,
+            num_tokens, chunks, key_stride * 2, value_stride * 2, block_stride * 2, row_bytes,
+            block_size);
+    } else {
+        const int threads = static_cast<int>(std::min<int64_t>(n, 512));
+        reshape_and_cache_flash_scalar_kernel<<<static_cast<unsigned>(num_tokens), threads, 0, stream>>>(
+            static_cast<const uint16_t *>(key), static_cast<const uint16_t *>(value),
+            static_cast<uint16_t *>(key_cache), static_cast<uint16_t *>(value_cache), slot_mapping,
+            block_stride, key_stride, value_stride, n, block_size);
+    }
+    note_launch();
+    check_launch("reshape_and_cache_flash");
+}
+
+extern "C" void swap_blocks_batched(void *dst_base, const void *src_base,
+                                    const int64_t *src_blocks, const int64_t *dst_blocks,
+                                    int64_t num_pairs, int64_t block_bytes, int kind,
+                                    atoma_stream_t stream_) {
+    clear_status();
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (num_pairs <= 0 || block_bytes <= 0) return;
+    if (kind == 0) {
+        // Device -> device: upload the mapping, one launch for all pairs.
+        int64_t *dmap = static_cast<int64_t *>(
+            get_workspace(stream, 2 * num_pairs * sizeof(int64_t), kWorkspaceSwapMap));
+        if (!dmap) return;
+        cudaMemcpyAsync(dmap, src_blocks, num_pairs * sizeof(int64_t), cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(dmap + num_pairs, dst_blocks, num_pairs * sizeof(int64_t),
+                        cudaMemcpyHostToDevice, stream);
+        if (block_bytes % 16 == 0 && aligned16(dst_base) && aligned16(src_base)) {
+            static thread_local int attr_dev = -1;
+            const DeviceInfo &di = current_device_info();
+            if (attr_dev != di.ordinal) {
+                cudaFuncSetAttribute(swap_blocks_bulk_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kRing * kPieceBytes);
+                attr_dev = di.ordinal;
+            }
+            swap_blocks_bulk_kernel<<<static_cast<unsigned>(num_pairs), 32, kRing * kPieceBytes, stream>>>(
+                static_cast<char *>(dst_base), static_cast<const char *>(src_base), dmap,
+                dmap + num_pairs, block_bytes);
+        } else {
+            swap_blocks_scalar_kernel<<<static_cast<unsigned>(num_pairs), 256, 0, stream>>>(
+                static_cast<char *>(dst_base), static_cast<const char *>(src_base), dmap,
+                dmap + num_pairs, block_bytes);
+        }
+        note_launch();
+        check_launch("swap_blocks_batched");
+        return;
+    }
+    if (kind != 1 && kind != 2) {
+        set_status(kErrInvalidArg, "swap_blocks_batched: kind %d (0 d2d, 1 h2d, 2 d2h)", kind);
+        return;
+    }
+    // Host <-> device: merge runs of consecutive (src, dst) blocks into single async copies.
+    std::vector<std::pair<int64_t, int64_t>> pairs(num_pairs);
+    for (int64_t i = 0; i < num_pairs; ++i) pairs[i] = {src_blocks[i], dst_blocks[i]};
+    std::sort(pairs.begin(), pairs.end());
+    const cudaMemcpyKind mk = kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    int64_t i = 0;
+    while (i < num_pairs) {
+        int64_t j = i + 1;
+        while (j < num_pairs && pairs[j].first == pairs[j - 1].first + 1 &&
+               pairs[j].second == pairs[j - 1].second + 1)
+            ++j;
+        cudaError_t e = cudaMemcpyAsync(static_cast<char *>(dst_base) + pairs[i].second * block_bytes,
+                                        static_cast<const char *>(src_base) + pairs[i].first * block_bytes,
+                                        static_cast<size_t>((j - i) * block_bytes), mk, stream);
+        if (e != cudaSuccess) {
+            set_status(static_cast<int>(e), "swap_blocks_batched: cudaMemcpyAsync: %s",
+                       cudaGetErrorString(e));
+            return;
+        }
+        i = j;
+    }
+}

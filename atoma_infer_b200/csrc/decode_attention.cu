@@ -1,0 +1,606 @@
+// Paged single-token decode attention for sm_100a (B200).
+//
+// Replaces, for run_mha calls with a block table and seqlen_q == 1, the reference's
+// flash_fwd_splitkv_kernel + flash_fwd_splitkv_combine_kernel pair
+// (csrc/kernels/flash_fwd_kernel.h:504-1092, :1131-1313, launched from
+// flash_fwd_launch_template.h:105-177) — "paged attention v1/v2" in BASELINE.json's wording.
+// Same contract: O[b,h,:] = softmax(scale * q[b,h,:] . K_b[:, h/G, :]^T) V_b over the first
+// seqlens_k[b] cached tokens, gathered through block_table[b, :]; fp32 scores/softmax, P rounded
+// to the 16-bit type before P.V, fp32 accumulation (flash_fwd_kernel.h:949-954).
+//
+// Design (nothing here is taken from the reference's FA2 kernel):
+//  * The work is the flat list of "stage units": (sequence, kv-head group, 128 cache rows).  A
+//    persistent grid of min(#SM, units) CTAs takes equal contiguous slices of that list
+//    (stream-K), so the 1.73-wave imbalance of one-CTA-per-(sequence, head) never appears and no
+//    caller-chosen num_splits is needed.
+//  * One producer warp streams K and V with TMA (cp.async.bulk.tensor, 128-byte swizzle) straight
+//    out of the reference's [num_blocks, block_size, num_kv_heads, head_size] cache layout: a box is
+//    [64 d][TB tokens][HKT heads] of one physical page, i.e. for Llama-3.1-8B two boxes cover one
+//    whole contiguous 32 KiB K page (all 8 kv heads).  Page ids are prefetched 32 at a time from
+//    the block table with one coalesced load and never past ceil(len / page) (the reference reads
+//    up to 7 entries past it).
+//  * Eight consumer warps each own one (kv head, 16-token) slice of a stage and run the GQA group
+//    of that kv head as the M dimension of mma.sync m16n8k16 (all H/Hkv query heads share one pass
+//    over K/V; the reference re-streams K/V once per query head).
+//  * Split partials (fp32 O, running max, running sum per warp) go to a library-owned L2-resident
+//    workspace; the last CTA to arrive for a (sequence, head group) reduces them and writes the
+//    16-bit output (+LSE) — one launch, no combine kernel.
+#include "common.cuh"
+#include "mha_params.h"
+
+#include <cstring>
+#include <vector>
+
+namespace atoma {
+namespace {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kDecodeThreads = kConsumerThreads + 32;  // + producer warp
+constexpr int kStageRows = 128;                        // (token, head) rows per stage
+constexpr int kMaxBatch = 2047;
+constexpr int kMaxCounters = 16384;                    // B * head groups
+constexpr int kPartRows = 16;                          // M of the mma tile
+
+template <int D>
+struct Cfg {
+    static constexpr int kHalves = D / 64;              // 128-byte column halves per row
+    static constexpr int kHalfBytes = kStageRows * 128; // 16 KiB
+    static constexpr int kTileBytes = kHalves * kHalfBytes;  // K (or V) bytes per stage
+    static constexpr int kStageBytes = 2 * kTileBytes;
+    static constexpr int kStages = (192 * 1024) / kStageBytes;  // 3 (D=128) / 6 (D=64)
+};
+
+struct DecodeArgs {
+    MhaParams p;
+    int hkt;         // kv heads per CTA tile (1, 2, 4, 8)
+    int hg;          // kv head groups = h_k / hkt
+    int tok;         // tokens per stage = 128 / hkt
+    int tb;          // tokens per TMA box (divides page and tok, multiple of 16)
+    int g;           // query heads per kv head
+    int num_ctas;
+    int *counters;   // [b * hg], zero between launches
+    float *ws_ml;    // [cta][2][8 warps][16 rows][2]
+    float *ws_o;     // [cta][2][8 warps][16 rows][D]
+};
+
+__device__ __forceinline__ int seq_len_k(const MhaParams &p, int b) {
+    int len;
+    if (p.seqused_k) len = p.seqused_k[b];
+    else if (p.cu_k) len = p.k_cumulative ? p.cu_k[b + 1] - p.cu_k[b] : p.cu_k[b];
+    else len = p.seqlen_k;
+    return max(0, min(len, p.seqlen_k));
+}
+
+__device__ __forceinline__ long long cta_start(long long units, int cta, int num_ctas) {
+    return units * cta / num_ctas;
+}
+// Largest c with cta_start(c) <= u.
+__device__ __forceinline__ int cta_of_unit(long long units, long long u, int num_ctas) {
+    return static_cast<int>(((u + 1) * num_ctas + units - 1) / units - 1);
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(kDecodeThreads, 1)
+decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, const DecodeArgs a) {
+    using C = Cfg<D>;
+    const MhaParams &p = a.p;
+    extern __shared__ unsigned char smem_dyn[];
+    // 128-byte-swizzled TMA destinations need 1024-byte alignment.
+    unsigned char *tiles = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    __shared__ __align__(8) uint64_t full_k[C::kStages], full_v[C::kStages], empty[C::kStages];
+    __shared__ int cum[kMaxBatch + 2];  // cum[b] = first unit of sequence b
+    __shared__ int combine_flag;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int B = p.b;
+
+    if (tid == 0) {
+        for (int i = 0; i < C::kStages; ++i) {
+            mbar_init(&full_k[i], 1);
+            mbar_init(&full_v[i], 1);
+            mbar_init(&empty[i], kConsumerWarps);
+        }
+        fence_mbar_init();
+    }
+    if (warp == kConsumerWarps && lane == 0) {
+        tma_prefetch_desc(&map_k);
+        tma_prefetch_desc(&map_v);
+    }
+    // units per sequence -> exclusive prefix sum in cum[]
+    for (int i = tid; i < B; i += kDecodeThreads) {
+        const int len = seq_len_k(p, i);
+        cum[i + 1] = a.hg * ((len + a.tok - 1) / a.tok);
+    }
+    if (tid == 0) cum[0] = 0;
+    __syncthreads();
+    if (warp == 0) {
+        int carry = 0;
+        for (int base = 0; base < B; base += 32) {
+            const int i = base + lane;
+            int v = i < B ? cum[i + 1] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += n;
+            }
+            if (i < B) cum[i + 1] = v + carry;
+            carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+    __syncthreads();
+    const long long units = cum[B];
+    const int cta = blockIdx.x;
+
+    // Sequences without any cached token: O = 0, LSE = +inf (flash_fwd_kernel.h:543-582).
+    for (int b = cta; b < B; b += gridDim.x) {
+        if (cum[b + 1] != cum[b]) continue;
+        T *ob = static_cast<T *>(p.o) + b * p.o_bs;
+        for (int i = tid; i < p.h * (D / 8); i += kDecodeThreads) {
+            const int hh = i / (D / 8), c = i % (D / 8);
+            *reinterpret_cast<uint4 *>(ob + hh * p.o_hs + c * 8) = make_uint4(0, 0, 0, 0);
+        }
+        if (p.lse)
+            for (int i = tid; i < p.h; i += kDecodeThreads) p.lse[static_cast<int64_t>(b) * p.h + i] = INFINITY;
+    }
+
+    // The grid was sized from the host-side upper bound of the unit count; only the first
+    // min(grid, units) CTAs take part in the partition, so that every participant owns >= 1 unit
+    // (the arrival-count logic below relies on it).
+    const int ncta = static_cast<int>(min(static_cast<long long>(gridDim.x), units));
+    if (cta >= ncta) return;
+    const long long u_begin = cta_start(units, cta, ncta), u_end = cta_start(units, cta + 1, ncta);
+
+    const int box_rows = a.hkt * a.tb;            // 128-byte lines per box
+    const uint32_t box_bytes = box_rows * 128u;
+    const int boxes_per_half = a.tok / a.tb;
+
+    int stage = 0;
+    uint32_t phase = 0;
+
+    if (warp == kConsumerWarps) {
+        // =========================== producer warp ===========================
+        long long u = u_begin;
+        int b = 0;
+        while (u < u_end) {
+            while (cum[b + 1] <= u) ++b;
+            const int ns = (cum[b + 1] - cum[b]) / a.hg;
+            const int r = static_cast<int>(u - cum[b]);
+            const int hg = r / ns, s0 = r % ns;
+            const int n = static_cast<int>(min(static_cast<long long>(ns - s0), u_end - u));
+            const int len = seq_len_k(p, b);
+            const int npages = (len + p.page - 1) / p.page;
+            const int *bt = p.block_table + b * p.bt_bs;
+            int pbase = -(1 << 30), pg_cache = 0;
+            for (int s = s0; s < s0 + n; ++s) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                __syncwarp();
+                const int tok0 = s * a.tok;
+                int nbx = (len - tok0 + a.tb - 1) / a.tb;
+                nbx = min(nbx, boxes_per_half);
+                unsigned char *ks = tiles + stage * C::kStageBytes;
+                unsigned char *vs = ks + C::kTileBytes;
+                if (lane == 0) mbar_arrive_expect_tx(&full_k[stage], nbx * C::kHalves * box_bytes);
+                int phys[8];
+#pragma unroll
+                for (int bx = 0; bx < 8; ++bx) {
+                    phys[bx] = 0;
+                    if (bx < nbx) {  // warp-uniform
+                        const int pi = (tok0 + bx * a.tb) / p.page;
+                        if (pi < pbase || pi >= pbase + 32) {
+                            pbase = pi;
+                            pg_cache = (pbase + lane < npages) ? bt[pbase + lane] : 0;
+                        }
+                        phys[bx] = __shfl_sync(0xffffffffu, pg_cache, pi - pbase);
+                    }
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int bx = 0; bx < 8; ++bx) {
+                        if (bx < nbx) {
+                            const int t_in_page = (tok0 + bx * a.tb) % p.page;
+#pragma unroll
+                            for (int hf = 0; hf < C::kHalves; ++hf)
+                                tma_load_4d(ks + hf * C::kHalfBytes + bx * box_bytes, &map_k,
+                                            &full_k[stage], hf * 64, t_in_page, hg * a.hkt, phys[bx],
+                                            kL2EvictFirst);
+                        }
+                    }
+                    mbar_arrive_expect_tx(&full_v[stage], nbx * C::kHalves * box_bytes);
+#pragma unroll
+                    for (int bx = 0; bx < 8; ++bx) {
+                        if (bx < nbx) {
+                            const int t_in_page = (tok0 + bx * a.tb) % p.page;
+#pragma unroll
+                            for (int hf = 0; hf < C::kHalves; ++hf)
+                                tma_load_4d(vs + hf * C::kHalfBytes + bx * box_bytes, &map_v,
+                                            &full_v[stage], hf * 64, t_in_page, hg * a.hkt, phys[bx],
+                                            kL2EvictFirst);
+                        }
+                    }
+                }
+                if (++stage == C::kStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            u += n;
+        }
+        return;
+    }
+
+    // ============================== consumer warps ==============================
+    const int g = lane >> 2, t4 = lane & 3;
+    const int hh = warp % a.hkt;          // kv head within the group
+    const int ts = warp / a.hkt;          // 16-token slice within the stage
+    const int bx_w = (ts * 16) / a.tb;    // box holding this warp's tokens
+    const int row_base = bx_w * box_rows + hh * a.tb + (ts * 16) % a.tb;  // 128-byte line index
+    const int G = a.g;
+
+    long long u = u_begin;
+    int b = 0;
+    while (u < u_end) {
+        while (cum[b + 1] <= u) ++b;
+        const int ns = (cum[b + 1] - cum[b]) / a.hg;
+        const int r = static_cast<int>(u - cum[b]);
+        const int hg = r / ns, s0 = r % ns;
+        const int n = static_cast<int>(min(static_cast<long long>(ns - s0), u_end - u));
+        const int len = seq_len_k(p, b);
+        const int kvh = hg * a.hkt + hh;
+
+        // ---- Q fragments (A operand): rows = the G query heads of kv head `kvh` ----
+        uint32_t qf[D / 16][4];
+        {
+            const T *qb = static_cast<const T *>(p.q) + b * p.q_bs;
+            const T *q0 = qb + static_cast<int64_t>(kvh * G + g) * p.q_hs;
+            const T *q1 = qb + static_cast<int64_t>(kvh * G + g + 8) * p.q_hs;
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk) {
+                const int d0 = kk * 16 + 2 * t4;
+                qf[kk][0] = g < G ? *reinterpret_cast<const uint32_t *>(q0 + d0) : 0u;
+                qf[kk][1] = g + 8 < G ? *reinterpret_cast<const uint32_t *>(q1 + d0) : 0u;
+                qf[kk][2] = g < G ? *reinterpret_cast<const uint32_t *>(q0 + d0 + 8) : 0u;
+                qf[kk][3] = g + 8 < G ? *reinterpret_cast<const uint32_t *>(q1 + d0 + 8) : 0u;
+            }
+        }
+        float o_acc[D / 8][4];
+#pragma unroll
+        for (int i = 0; i < D / 8; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
+        float m_run[2] = {-INFINITY, -INFINITY};
+        float l_run[2] = {0.f, 0.f};
+
+        for (int s = s0; s < s0 + n; ++s) {
+            const uint32_t ks = smem_u32(tiles + stage * C::kStageBytes);
+            const uint32_t vs = ks + C::kTileBytes;
+            const int nvalid = len - (s * a.tok + ts * 16);  // valid tokens in this warp's slice
+            mbar_wait(&full_k[stage], phase);
+            if (nvalid > 0) {
+                // ---- S = Q K^T : 16 (heads, padded) x 16 tokens ----
+                float sc[2][4];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+                {
+                    const int i = (lane >> 4) * 8 + (lane & 7);  // token within the slice
+                    const uint32_t line = ks + (row_base + i) * 128;
+#pragma unroll
+                    for (int kk = 0; kk < D / 16; ++kk) {
+                        const int c = kk * 2 + ((lane >> 3) & 1);  // 16-byte chunk over D
+                        uint32_t bf[4];
+                        ldmatrix_x4(bf, line + (c >> 3) * C::kHalfBytes + (((c & 7) ^ (lane & 7)) << 4));
+                        Mma16816<T>::run(sc[0], qf[kk], bf[0], bf[1]);
+                        Mma16816<T>::run(sc[1], qf[kk], bf[2], bf[3]);
+                    }
+                }
+                // ---- online softmax (log2 domain) ----
+                float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int tokc = j * 8 + 2 * t4 + (e & 1);
+                        float x = sc[j][e] * p.scale_log2;
+                        x = tokc < nvalid ? x : -INFINITY;
+                        sc[j][e] = x;
+                        mx[e >> 1] = fmaxf(mx[e >> 1], x);
+                    }
+                }
+                float corr[2], m_safe[2];
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    mx[rr] = fmaxf(mx[rr], __shfl_xor_sync(0xffffffffu, mx[rr], 1));
+                    mx[rr] = fmaxf(mx[rr], __shfl_xor_sync(0xffffffffu, mx[rr], 2));
+                    const float m_new = fmaxf(m_run[rr], mx[rr]);
+                    m_safe[rr] = m_new == -INFINITY ? 0.f : m_new;
+                    corr[rr] = fast_exp2(m_run[rr] - m_safe[rr]);
+                    m_run[rr] = m_new;
+                }
+                float rs[2] = {0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float pv = fast_exp2(sc[j][e] - m_safe[e >> 1]);
+                        sc[j][e] = pv;
+                        rs[e >> 1] += pv;
+                    }
+                }
+                l_run[0] = l_run[0] * corr[0] + rs[0];
+                l_run[1] = l_run[1] * corr[1] + rs[1];
+                if (__any_sync(0xffffffffu, corr[0] != 1.f || corr[1] != 1.f)) {
+#pragma unroll
+                    for (int i = 0; i < D / 8; ++i) {
+                        o_acc[i][0] *= corr[0];
+                        o_acc[i][1] *= corr[0];
+                        o_acc[i][2] *= corr[1];
+                        o_acc[i][3] *= corr[1];
+                    }
+                }
+                uint32_t pa[4];
+                pa[0] = pack2<T>(sc[0][0], sc[0][1]);
+                pa[1] = pack2<T>(sc[0][2], sc[0][3]);
+                pa[2] = pack2<T>(sc[1][0], sc[1][1]);
+                pa[3] = pack2<T>(sc[1][2], sc[1][3]);
+
+                mbar_wait(&full_v[stage], phase);
+                if (nvalid < 16) {
+                    // Ragged tail: cache rows past the sequence may hold anything (NaN included) and
+                    // 0 * NaN would poison the accumulator: clear them (the reference zero-fills its
+                    // V tile instead, flash_fwd_kernel.h:901-906).
+                    for (int idx = lane; idx < 16 * (D / 8); idx += 32) {
+                        const int i = idx / (D / 8), c = idx % (D / 8);
+                        if (i >= nvalid)
+                            *reinterpret_cast<uint4 *>(tiles + (vs - smem_u32(tiles)) +
+                                                       (c >> 3) * C::kHalfBytes + (row_base + i) * 128 +
+                                                       (((c & 7) ^ (i & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+                    }
+                    __syncwarp();
+                }
+                // ---- O += P V ----
+                {
+                    const int i = ((lane >> 3) & 1) * 8 + (lane & 7);
+                    const uint32_t line = vs + (row_base + i) * 128;
+#pragma unroll
+                    for (int dj2 = 0; dj2 < D / 16; ++dj2) {
+                        const int c = dj2 * 2 + (lane >> 4);
+                        uint32_t vf[4];
+                        ldmatrix_x4_trans(vf, line + (c >> 3) * C::kHalfBytes + (((c & 7) ^ (lane & 7)) << 4));
+                        Mma16816<T>::run(o_acc[2 * dj2], pa, vf[0], vf[1]);
+                        Mma16816<T>::run(o_acc[2 * dj2 + 1], pa, vf[2], vf[3]);
+                    }
+                }
+                if (nvalid < 16) fence_proxy_async();
+            } else {
+                mbar_wait(&full_v[stage], phase);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == C::kStages) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+
+        // ---- publish this warp's partial ----
+        const long long ub = cum[b] + static_cast<long long>(hg) * ns, ue = ub + ns;
+        const int slot = (u_begin >= ub && u_begin < ue) ? 0 : 1;  // first segment of the CTA -> 0
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            l_run[rr] += __shfl_xor_sync(0xffffffffu, l_run[rr], 1);
+            l_run[rr] += __shfl_xor_sync(0xffffffffu, l_run[rr], 2);
+        }
+        {
+            const int64_t part = (static_cast<int64_t>(cta) * 2 + slot) * kConsumerWarps + warp;
+            float *po = a.ws_o + part * (kPartRows * D);
+            float *pml = a.ws_ml + part * (kPartRows * 2);
+            if (g < G) {
+#pragma unroll
+                for (int dj = 0; dj < D / 8; ++dj)
+                    __stcg(reinterpret_cast<float2 *>(po + g * D + dj * 8 + 2 * t4),
+                           make_float2(o_acc[dj][0], o_acc[dj][1]));
+                if (t4 == 0) __stcg(reinterpret_cast<float2 *>(pml + g * 2), make_float2(m_run[0], l_run[0]));
+            }
+            if (g + 8 < G) {
+#pragma unroll
+                for (int dj = 0; dj < D / 8; ++dj)
+                    __stcg(reinterpret_cast<float2 *>(po + (g + 8) * D + dj * 8 + 2 * t4),
+                           make_float2(o_acc[dj][2], o_acc[dj][3]));
+                if (t4 == 0)
+                    __stcg(reinterpret_cast<float2 *>(pml + (g + 8) * 2), make_float2(m_run[1], l_run[1]));
+            }
+        }
+        __threadfence();
+        named_bar_sync(1, kConsumerThreads);
+        const int fc = cta_of_unit(units, ub, ncta), lc = cta_of_unit(units, ue - 1, ncta);
+        if (tid == 0) {
+            const int old = atomicAdd(&a.counters[b * a.hg + hg], 1);
+            combine_flag = (old == lc - fc) ? 1 : 0;
+        }
+        named_bar_sync(1, kConsumerThreads);
+        if (combine_flag) {
+            // ---- last arriver: reduce every partial of (b, hg) and write the output ----
+            __threadfence();
+            const int wpk = kConsumerWarps / a.hkt;  // warps (token slices) per kv head
+            const int total = a.hkt * G * (D / 4);
+            for (int idx = tid; idx < total; idx += kConsumerThreads) {
+                const int d4 = idx % (D / 4);
+                const int rr = (idx / (D / 4)) % G;
+                const int h2 = idx / (D / 4) / G;
+                float m_star = -INFINITY;
+                for (int c = fc; c <= lc; ++c) {
+                    const long long cs = cta_start(units, c, ncta);
+                    const int sl = (cs >= ub && cs < ue) ? 0 : 1;
+                    for (int w = 0; w < wpk; ++w) {
+                        const int64_t part = (static_cast<int64_t>(c) * 2 + sl) * kConsumerWarps + w * a.hkt + h2;
+                        m_star = fmaxf(m_star, __ldcg(a.ws_ml + part * (kPartRows * 2) + rr * 2));
+                    }
+                }
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                float lsum = 0.f;
+                if (m_star != -INFINITY) {
+                    for (int c = fc; c <= lc; ++c) {
+                        const long long cs = cta_start(units, c, ncta);
+                        const int sl = (cs >= ub && cs < ue) ? 0 : 1;
+                        for (int w = 0; w < wpk; ++w) {
+                            const int64_t part =
+                                (static_cast<int64_t>(c) * 2 + sl) * kConsumerWarps + w * a.hkt + h2;
+                            const float2 ml = __ldcg(reinterpret_cast<const float2 *>(
+                                a.ws_ml + part * (kPartRows * 2) + rr * 2));
+                            if (ml.x == -INFINITY) continue;
+                            const float wgt = fast_exp2(ml.x - m_star);
+                            const float4 ov = __ldcg(reinterpret_cast<const float4 *>(
+                                a.ws_o + part * (kPartRows * D) + rr * D + d4 * 4));
+                            acc.x += wgt * ov.x;
+                            acc.y += wgt * ov.y;
+                            acc.z += wgt * ov.z;
+                            acc.w += wgt * ov.w;
+                            lsum += wgt * ml.y;
+                        }
+                    }
+                }
+                const float inv = (lsum == 0.f || lsum != lsum) ? 1.f : 1.f / lsum;
+                const int head = (hg * a.hkt + h2) * G + rr;
+                T *op = static_cast<T *>(p.o) + b * p.o_bs + static_cast<int64_t>(head) * p.o_hs + d4 * 4;
+                uint2 packed;
+                packed.x = pack2<T>(acc.x * inv, acc.y * inv);
+                packed.y = pack2<T>(acc.z * inv, acc.w * inv);
+                *reinterpret_cast<uint2 *>(op) = packed;
+                if (d4 == 0 && p.lse)
+                    p.lse[static_cast<int64_t>(b) * p.h + head] =
+                        (lsum == 0.f || lsum != lsum) ? INFINITY
+                                                      : m_star * 0.6931471805599453f + __logf(lsum);
+            }
+            if (tid == 0) a.counters[b * a.hg + hg] = 0;  // self-cleaning for the next launch
+        }
+        named_bar_sync(1, kConsumerThreads);  // combine_flag / slot 1 may be reused by the next segment
+        u += n;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+struct MapKey {
+    const void *ptr;
+    int64_t rs, hs, bs;
+    int page, hk, d, tb, hkt, bf16;
+    bool operator==(const MapKey &o) const { return std::memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapEntry {
+    MapKey key;
+    CUtensorMap map;
+};
+
+bool make_kv_map(CUtensorMap *out, const void *ptr, int64_t rs, int64_t hs, int64_t bs, int page,
+                 int hk, int d, int tb, int hkt, bool is_bf16) {
+    static thread_local std::vector<MapEntry> cache;
+    MapKey key;
+    std::memset(&key, 0, sizeof(key));
+    key.ptr = ptr; key.rs = rs; key.hs = hs; key.bs = bs; key.page = page; key.hk = hk; key.d = d;
+    key.tb = tb; key.hkt = hkt; key.bf16 = is_bf16;
+    for (const MapEntry &e : cache)
+        if (e.key == key) { *out = e.map; return true; }
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return false;
+    // dims, fastest first: d, token-in-page, kv head, physical page.  The page count is not part of
+    // the run_mha ABI; any id the block table can hold must be addressable.
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(page),
+                                static_cast<cuuint64_t>(hk), static_cast<cuuint64_t>(1) << 22};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(rs) * 2, static_cast<cuuint64_t>(hs) * 2,
+                                   static_cast<cuuint64_t>(bs) * 2};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(tb), static_cast<cuuint32_t>(hkt), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                     const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_status(kErrDriver, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
+        return false;
+    }
+    if (cache.size() >= 256) cache.clear();
+    cache.push_back(MapEntry{key, *out});
+    return true;
+}
+
+template <typename T, int D>
+bool launch_decode(const CUtensorMap &mk, const CUtensorMap &mv, const DecodeArgs &a,
+                   cudaStream_t stream) {
+    constexpr size_t smem = Cfg<D>::kStages * Cfg<D>::kStageBytes + 1024;
+    static thread_local int attr_dev = -1;
+    const DeviceInfo &di = current_device_info();
+    if (attr_dev != di.ordinal) {
+        cudaFuncSetAttribute(decode_paged_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem));
+        attr_dev = di.ordinal;
+    }
+    decode_paged_kernel<T, D><<<a.num_ctas, kDecodeThreads, smem, stream>>>(mk, mv, a);
+    note_launch();
+    return check_launch("decode_paged_kernel");
+}
+
+}  // namespace
+
+// Returns 1 if the decode kernel took the call, 0 if the configuration is outside its envelope
+// (caller falls back to the general tile kernel), -1 on error (status set).
+int try_launch_decode_paged(const MhaParams &p, bool is_bf16, int64_t max_units_hint,
+                            cudaStream_t stream) {
+    if (!p.block_table || p.seqlen_q != 1 || p.alibi || p.cu_q) return 0;
+    if (p.d != 64 && p.d != 128) return 0;
+    if (p.h_k <= 0 || p.h % p.h_k != 0) return 0;
+    const int G = p.h / p.h_k;
+    if (G > 16 || p.b > kMaxBatch || p.b <= 0) return 0;
+    if (p.page <= 0 || p.page % 16 != 0) return 0;
+    auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (!al16(p.k) || !al16(p.v) || !al16(p.o)) return 0;
+    if ((reinterpret_cast<uintptr_t>(p.q) & 3) != 0) return 0;
+    if (p.k_rs % 8 || p.k_hs % 8 || p.k_bs % 8 || p.v_rs % 8 || p.v_hs % 8 || p.v_bs % 8) return 0;
+    if (p.q_hs % 2 || p.q_bs % 2 || p.o_hs % 8 || p.o_bs % 8) return 0;
+    if (p.k_rs * 2 >= (1ll << 40) || p.k_bs * 2 >= (1ll << 40)) return 0;
+
+    int hkt = 8;
+    while (hkt > 1 && p.h_k % hkt != 0) hkt >>= 1;
+    const int hg = p.h_k / hkt;
+    if (static_cast<int64_t>(p.b) * hg > kMaxCounters) return 0;
+    const int tok = kStageRows / hkt;
+    int tb = tok;
+    while (tb > 16 && p.page % tb != 0) tb >>= 1;
+    if (tok / tb > 8) return 0;
+
+    const DeviceInfo &di = current_device_info();
+    if (di.cc_major < 9) {
+        set_status(kErrUnsupported, "decode kernel needs TMA (sm_90+), device is sm_%d%d", di.cc_major, di.cc_minor);
+        return -1;
+    }
+    DecodeArgs a;
+    a.p = p;
+    a.hkt = hkt; a.hg = hg; a.tok = tok; a.tb = tb; a.g = G;
+    // Upper bound on units is known on the host only through seqlen_k (= pages * page size); the
+    // kernel derives the real count from the device-side lengths.  Grid: one CTA per SM, but never
+    // more CTAs than the upper bound of units.
+    const int64_t units_ub = static_cast<int64_t>(p.b) * hg * ((p.seqlen_k + tok - 1) / tok);
+    (void)max_units_hint;
+    a.num_ctas = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(di.sm_count, units_ub)));
+
+    const size_t counters_bytes = kMaxCounters * sizeof(int);
+    const size_t ml_bytes = static_cast<size_t>(di.sm_count) * 2 * kConsumerWarps * kPartRows * 2 * sizeof(float);
+    const size_t o_bytes = static_cast<size_t>(di.sm_count) * 2 * kConsumerWarps * kPartRows * 128 * sizeof(float);
+    char *ws = static_cast<char *>(get_workspace(stream, counters_bytes + ml_bytes + o_bytes, kWorkspaceDecode));
+    if (!ws) return -1;
+    a.counters = reinterpret_cast<int *>(ws);
+    a.ws_ml = reinterpret_cast<float *>(ws + counters_bytes);
+    a.ws_o = reinterpret_cast<float *>(ws + counters_bytes + ml_bytes);
+
+    CUtensorMap mk, mv;
+    if (!make_kv_map(&mk, p.k, p.k_rs, p.k_hs, p.k_bs, p.page, p.h_k, p.d, tb, hkt, is_bf16)) return -1;
+    if (!make_kv_map(&mv, p.v, p.v_rs, p.v_hs, p.v_bs, p.page, p.h_k, p.d, tb, hkt, is_bf16)) return -1;
+
+    bool ok;
+    if (is_bf16) ok = p.d == 128 ? launch_decode<__nv_bfloat16, 128>(mk, mv, a, stream)
+                                 : launch_decode<__nv_bfloat16, 64>(mk, mv, a, stream);
+    else ok = p.d == 128 ? launch_decode<__half, 128>(mk, mv, a, stream)
+                         : launch_decode<__half, 64>(mk, mv, a, stream);
+    return ok ? 1 : -1;
+}
+
+}  // namespace atoma

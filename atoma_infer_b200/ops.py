@@ -1,0 +1,277 @@
+"""Python face of the host operator layer — same names, argument meaning and error behaviour as the
+reference's Rust crate `csrc` (csrc/src/lib.rs pub fns :392-2105, csrc/src/cache_manager.rs).
+
+Everything here is a thin shim: tensors are described to the C ABI (include/atoma_ops.h), the C++
+host layer validates / derives the `run_mha` arguments, and the CUDA kernels do the work.  torch is
+used for device memory and streams only.  There is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import MhaPlan, Tensor
+
+
+class AtomaError(RuntimeError):
+    """The analogue of `candle_core::Error` raised by `bail!` in the reference wrappers."""
+
+
+_DTYPES = {
+    torch.float16: _lib.F16,
+    torch.bfloat16: _lib.BF16,
+    torch.float32: _lib.F32,
+    torch.int32: _lib.U32,  # candle has no i32; u32 tensors travel as int32 bit patterns
+    torch.int64: _lib.I64,
+    torch.uint8: _lib.U8,
+    torch.float64: _lib.F64,
+}
+if hasattr(torch, "uint32"):
+    _DTYPES[torch.uint32] = _lib.U32
+
+
+def desc(t: Optional[torch.Tensor], device: Optional[int] = None) -> Optional[Tensor]:
+    """Describe a torch tensor (pointer already includes the storage offset)."""
+    if t is None:
+        return None
+    if t.dim() > _lib.MAX_RANK:
+        raise AtomaError(f"rank {t.dim()} tensors are not supported")
+    d = Tensor()
+    d.data = t.data_ptr()
+    d.dtype = _DTYPES[t.dtype]
+    if device is None:
+        device = t.device.index if t.is_cuda else _lib.DEVICE_CPU
+        if t.is_cuda and device is None:
+            device = torch.cuda.current_device()
+    d.device = device
+    d.rank = t.dim()
+    for i in range(t.dim()):
+        d.shape[i] = t.shape[i]
+        d.stride[i] = t.stride(i)
+    return d
+
+
+def spec(shape: Sequence[int], dtype: int, device: int = 0, stride: Optional[Sequence[int]] = None,
+         data: int = 0x1000) -> Tensor:
+    """A descriptor without memory behind it (plan-only calls: argument-derivation tests)."""
+    d = Tensor()
+    d.data = data
+    d.dtype = dtype
+    d.device = device
+    d.rank = len(shape)
+    if stride is None:
+        stride, acc = [0] * len(shape), 1
+        for i in reversed(range(len(shape))):
+            stride[i] = acc
+            acc *= shape[i]
+    for i, (s, st) in enumerate(zip(shape, stride)):
+        d.shape[i] = s
+        d.stride[i] = st
+    return d
+
+
+def _as_desc(t) -> Optional[Tensor]:
+    if t is None or isinstance(t, Tensor):
+        return t
+    return desc(t)
+
+
+def _ref(d: Optional[Tensor]):
+    return C.byref(d) if d is not None else None
+
+
+def _check(msg: Optional[bytes]) -> None:
+    if msg:
+        raise AtomaError(msg.decode())
+
+
+def _opt(v: Optional[int]) -> int:
+    return -1 if v is None else int(v)
+
+
+def _stream(t: Optional[torch.Tensor] = None) -> int:
+    if torch.cuda.is_available():
+        return torch.cuda.current_stream().cuda_stream
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# plans (argument derivation; run anywhere, no GPU needed)
+# ------------------------------------------------------------------------------------------------
+def flash_attn_plan(q, k, v, softmax_scale: float, window_size_left=None, window_size_right=None,
+                    alibi_slopes=None, softcap: Optional[float] = None, num_sms: int = 0) -> MhaPlan:
+    plan = MhaPlan()
+    qd, kd, vd, ad = map(_as_desc, (q, k, v, alibi_slopes))
+    _check(_lib.lib().atoma_flash_attn_plan(_ref(qd), _ref(kd), _ref(vd), _ref(ad), softmax_scale,
+                                            _opt(window_size_left), _opt(window_size_right),
+                                            softcap or 0.0, num_sms, C.byref(plan)))
+    return plan
+
+
+def flash_attn_varlen_plan(q, k, v, seqlens_q, seqlens_k, max_seqlen_q: int, max_seqlen_k: int,
+                           softmax_scale: float, window_size_left=None, window_size_right=None,
+                           alibi_slopes=None, seqused_k=None, block_table=None,
+                           softcap: Optional[float] = None, num_sms: int = 0) -> MhaPlan:
+    plan = MhaPlan()
+    ds = list(map(_as_desc, (q, k, v, alibi_slopes, seqlens_q, seqlens_k, seqused_k, block_table)))
+    _check(_lib.lib().atoma_flash_attn_varlen_plan(*[_ref(d) for d in ds], max_seqlen_q, max_seqlen_k,
+                                                   softmax_scale, _opt(window_size_left),
+                                                   _opt(window_size_right), softcap or 0.0, num_sms,
+                                                   C.byref(plan)))
+    return plan
+
+
+def flash_attn_kv_cache_plan(q, k_cache, v_cache, softmax_scale: float, alibi_slopes=None,
+                             block_table=None, seqlens_k=None, window_size_left=None,
+                             window_size_right=None, num_sms: int = 0) -> MhaPlan:
+    plan = MhaPlan()
+    ds = list(map(_as_desc, (q, k_cache, v_cache, alibi_slopes, block_table, seqlens_k)))
+    _check(_lib.lib().atoma_flash_attn_kv_cache_plan(*[_ref(d) for d in ds], softmax_scale,
+                                                     _opt(window_size_left), _opt(window_size_right),
+                                                     num_sms, C.byref(plan)))
+    return plan
+
+
+def compute_num_splits(batch_size, num_heads, head_size, max_seqlen_k, max_seqlen_q, num_sms) -> int:
+    return _lib.lib().atoma_compute_num_splits(batch_size, num_heads, head_size, max_seqlen_k,
+                                               max_seqlen_q, num_sms)
+
+
+def _execute(plan: MhaPlan, like: torch.Tensor, *, legacy_stream: bool = False,
+             with_lse: bool = False):
+    shape = [plan.out_shape[i] for i in range(plan.out_rank)]
+    out = torch.empty(shape, dtype=like.dtype, device=like.device)  # uninitialised, like the reference
+    lse = None
+    if with_lse:
+        lse = torch.zeros(plan.lse_elems, dtype=torch.float32, device=like.device)
+    if legacy_stream:
+        torch.cuda.current_stream().synchronize()
+    _check(_lib.lib().atoma_mha_execute(C.byref(plan), out.data_ptr(), lse.data_ptr() if with_lse else None,
+                                        None, None, 1 if legacy_stream else 0, _stream()))
+    if legacy_stream:
+        torch.cuda.synchronize()
+    return (out, lse) if with_lse else out
+
+
+# ------------------------------------------------------------------------------------------------
+# csrc::flash_attn*  (csrc/src/lib.rs:392-571)
+# ------------------------------------------------------------------------------------------------
+def flash_attn(q, k, v, softmax_scale: float, causal: bool, **kw):
+    """q [b, sq, h, d]; k, v [b, sk, hk, d] -> [b, sq, h, d]   (lib.rs:392-410)"""
+    plan = flash_attn_plan(q, k, v, softmax_scale, None, 0 if causal else None)
+    return _execute(plan, q, **kw)
+
+
+def flash_attn_windowed(q, k, v, softmax_scale, window_size_left, window_size_right, **kw):
+    plan = flash_attn_plan(q, k, v, softmax_scale, window_size_left, window_size_right)
+    return _execute(plan, q, **kw)
+
+
+def flash_attn_alibi(q, k, v, alibi_slopes, softmax_scale, causal: bool, **kw):
+    plan = flash_attn_plan(q, k, v, softmax_scale, None, 0 if causal else None, alibi_slopes=alibi_slopes)
+    return _execute(plan, q, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# csrc::flash_attn_varlen*  (csrc/src/lib.rs:1160-1501)
+# ------------------------------------------------------------------------------------------------
+def flash_attn_varlen(q, k, v, seqlens_q, seqlens_k, max_seqlen_q: int, max_seqlen_k: int,
+                      softmax_scale: float, causal: bool, **kw):
+    """q [total_q, h, d]; k, v [total_k, hk, d]; cumulative u32 seqlens [b+1]   (lib.rs:1160-1188)"""
+    plan = flash_attn_varlen_plan(q, k, v, seqlens_q, seqlens_k, max_seqlen_q, max_seqlen_k, softmax_scale,
+                                  None, 0 if causal else None)
+    return _execute(plan, q, **kw)
+
+
+def flash_attn_varlen_with_block_table(q, k, v, alibi_slopes, seqlens_q, seqlens_k, max_seqlen_q: int,
+                                       max_seqlen_k: int, softmax_scale: float, window_size_left,
+                                       window_size_right, block_table, **kw):
+    """k, v [num_blocks, page, hk, d] gathered through block_table [b, max_blocks]  (lib.rs:1392-1420)"""
+    plan = flash_attn_varlen_plan(q, k, v, seqlens_q, seqlens_k, max_seqlen_q, max_seqlen_k, softmax_scale,
+                                  window_size_left, window_size_right, alibi_slopes=alibi_slopes,
+                                  block_table=block_table)
+    return _execute(plan, q, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# csrc::flash_attn_kv_cache*  (csrc/src/lib.rs:1907-2105)
+# ------------------------------------------------------------------------------------------------
+def flash_attn_kv_cache(q, k, v, softmax_scale: float, causal: bool, **kw):
+    plan = flash_attn_kv_cache_plan(q, k, v, softmax_scale, window_size_left=None,
+                                    window_size_right=0 if causal else None)
+    return _execute(plan, q, **kw)
+
+
+def flash_attn_kv_cache_full(q, k, v, alibi_slopes, softmax_scale: float, block_table, seqlens_k,
+                             causal: bool, **kw):
+    """q [b, sq, h, d]; caches [num_blocks, page, hk, d] (+block_table) or [b, sk, hk, d];
+    seqlens_k u32 [b] per-sequence lengths   (lib.rs:2083-2105)"""
+    plan = flash_attn_kv_cache_plan(q, k, v, softmax_scale, alibi_slopes=alibi_slopes, block_table=block_table,
+                                    seqlens_k=seqlens_k, window_size_left=None,
+                                    window_size_right=0 if causal else None)
+    return _execute(plan, q, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# cache ops  (csrc/src/cache_manager.rs)
+# ------------------------------------------------------------------------------------------------
+def reshape_and_cache_flash(key, value, key_cache, value_cache, slot_mapping) -> None:
+    """cache_manager.rs:319-535"""
+    ds = [desc(t) for t in (key, value, key_cache, value_cache, slot_mapping)]
+    _check(_lib.lib().atoma_reshape_and_cache_flash(*[_ref(d) for d in ds], _stream()))
+
+
+def copy_blocks(key_caches: Sequence[torch.Tensor], value_caches: Sequence[torch.Tensor],
+                block_mapping: torch.Tensor) -> None:
+    """cache_manager.rs:148-307 — block_mapping: device i64 [num_pairs, 2]"""
+    nk, nv = len(key_caches), len(value_caches)
+    karr = (Tensor * max(nk, 1))(*[desc(t) for t in key_caches])
+    varr = (Tensor * max(nv, 1))(*[desc(t) for t in value_caches])
+    scratch = None
+    if nk and key_caches[0].is_cuda:
+        scratch = torch.empty(2 * max(nk, nv), dtype=torch.int64, device=key_caches[0].device)
+    bm = desc(block_mapping)
+    _check(_lib.lib().atoma_copy_blocks(karr, nk, varr, nv, _ref(bm),
+                                        scratch.data_ptr() if scratch is not None else None, _stream()))
+    if scratch is not None:
+        scratch.record_stream(torch.cuda.current_stream())
+
+
+def swap_blocks(src: torch.Tensor, dst: torch.Tensor, block_mapping: Dict[int, int]) -> None:
+    """cache_manager.rs:18-128 — dst[block d] = src[block s] for (s, d) in block_mapping"""
+    n = len(block_mapping)
+    sb = (C.c_int64 * max(n, 1))(*block_mapping.keys())
+    db = (C.c_int64 * max(n, 1))(*block_mapping.values())
+    sd, dd = desc(src), desc(dst)
+    _check(_lib.lib().atoma_swap_blocks(_ref(sd), _ref(dd), sb, db, n, _stream()))
+    if src.is_cuda != dst.is_cuda:
+        torch.cuda.current_stream().synchronize()  # host buffers are usable on return, like the reference
+
+
+def gemm_bf16_tn(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y[T, N] = x[T, K] @ w[N, K]^T (bf16, fp32 accumulate): models/src/llama.rs:269-271, 311"""
+    T, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((T, N), dtype=x.dtype, device=x.device)
+    L = _lib.lib()
+    L.atoma_gemm_bf16_tn(x.data_ptr(), w.data_ptr(), out.data_ptr(), T, N, K, x.stride(0), w.stride(0),
+                         out.stride(0), _stream())
+    if L.atoma_last_status() != 0:
+        raise AtomaError(L.atoma_last_error().decode())
+    return out
+
+
+def last_mha_path() -> str:
+    return _lib.lib().atoma_last_mha_path().decode()
+
+
+def launch_count() -> int:
+    return _lib.lib().atoma_launch_count()
+
+
+def reset_launch_count() -> None:
+    _lib.lib().atoma_reset_launch_count()

@@ -1,0 +1,158 @@
+/*
+ * atoma_flash.h — C ABI of the B200-native attention / KV-cache library (libflashattention).
+ *
+ * Part 1 is the DROP-IN BOUNDARY: the four symbols the reference's Rust crate `csrc` binds in
+ * csrc/src/ffi.rs:3-102 (C side: csrc/kernels/flash_api.cu:22-82, cache_manager.cu:44-51, 64-71,
+ * 215-233).  Names, argument order and argument types are identical, so the reference's
+ * `libflashattention.a` can be swapped for this library without touching ffi.rs.
+ *
+ * Part 2 are extensions a B200 build wants behind the same Rust functions (explicit stream,
+ * batched swap, dense GEMM); each one names the reference call site it replaces.
+ *
+ * Conventions shared with the reference: every entry returns void, never allocates or frees
+ * caller memory, never synchronises the host; strides are in ELEMENTS; all pointers are device
+ * pointers unless said otherwise.  Errors (unsupported configuration, CUDA launch failure) are
+ * reported on stderr and recorded in a thread-local status readable with atoma_last_status().
+ */
+#ifndef ATOMA_FLASH_H_
+#define ATOMA_FLASH_H_
+
+#include <stdbool.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Opaque CUDA stream handle (cudaStream_t / CUstream). */
+typedef void *atoma_stream_t;
+
+/* ------------------------------------------------------------------------------------------ */
+/* Part 1 — the reference's C ABI (csrc/src/ffi.rs)                                            */
+/* ------------------------------------------------------------------------------------------ */
+
+/*
+ * Attention forward.  Replaces csrc/kernels/flash_api.cu:22-159 (`run_mha`), bound at
+ * csrc/src/ffi.rs:4-66 and called from csrc/src/lib.rs:283 (dense), :1043 (varlen / paged varlen)
+ * and :1801 (kv-cache decode).  Launches on the legacy default stream, as the reference does
+ * (flash_api.cu:157).
+ *
+ *   O = softmax(softmax_scale * Q K^T [+ alibi] [+ causal mask]) V        (fp32 softmax, 16-bit io)
+ *
+ *  - q/o are indexed  [batch * batch_stride | cu_seqlens_q[b] * row_stride] + row*row_stride
+ *    + head*head_stride + d;  k/v likewise, or through `block_table` when it is non-NULL:
+ *    token t of sequence b lives at k + block_table[b*block_table_batch_stride + t/page_block_size]
+ *    * k_batch_stride + (t % page_block_size) * k_row_stride          (reference utils.h:296-314).
+ *  - cu_seqlens_k is cumulative [b+1] when is_seqlens_k_cumulative, else per-sequence lengths [b]
+ *    (reference block_info.h:14-24); seqused_k, when non-NULL, overrides the key length.
+ *  - kv head of query head h is h / (h / h_k)                         (flash_fwd_kernel.h:593).
+ *  - causal mask is bottom-right aligned: key j visible to query i iff j <= i + len_k - len_q
+ *    (mask.h:171-172).  window_size_*, softcap are accepted and ignored exactly as the reference
+ *    ignores them (static_switch.h:7-11).
+ *  - softmax_lse (fp32) is written as [b,h,seqlen_q] when !unpadded_lse, as [h,total_q] otherwise.
+ *  - num_splits / softmax_lseaccum_ptr / oaccum_ptr are accepted for ABI compatibility; the split
+ *    policy is owned by the library (in-kernel reduction), the caller's accumulators are not used.
+ */
+void run_mha(void *q_ptr, void *k_ptr, void *v_ptr, void *o_ptr, void *softmax_lse_ptr,
+             void *alibi_slopes_ptr, int32_t *cu_seqlens_q_ptr, int32_t *cu_seqlens_k_ptr,
+             bool is_seqlens_k_cumulative, uint32_t q_batch_stride, uint32_t k_batch_stride,
+             uint32_t v_batch_stride, uint32_t o_batch_stride, uint32_t alibi_slopes_batch_stride,
+             uint32_t q_row_stride, uint32_t k_row_stride, uint32_t v_row_stride,
+             uint32_t o_row_stride, uint32_t q_head_stride, uint32_t k_head_stride,
+             uint32_t v_head_stride, uint32_t o_head_stride, uint32_t num_splits, uint32_t b,
+             uint32_t h, uint32_t h_k, uint32_t d, uint32_t d_rounded, float softmax_scale,
+             float scale_softmax_log2, int *block_table, uint32_t block_table_batch_stride,
+             int page_block_size, int *seqused_k, uint32_t seqlen_q, uint32_t seqlen_k,
+             uint32_t seqlen_q_rounded, uint32_t seqlen_k_rounded, int is_bf16, int is_causal,
+             int window_size_left, int window_size_right, float softcap, bool unpadded_lse,
+             bool force_split_kernel, void *softmax_lseaccum_ptr, void *oaccum_ptr);
+
+/*
+ * For every layer l < num_layers and pair p < num_pairs copy block src=block_mapping[2p] onto
+ * dst=block_mapping[2p+1] in BOTH the key cache and the value cache of layer l.
+ * key_cache_ptrs / value_cache_ptrs: device arrays of int64 base addresses [num_layers];
+ * block_mapping: device int64 [num_pairs, 2]; numel_per_block counts 2-byte elements.
+ * Replaces cache_manager.cu:16-81, bound at ffi.rs:68-86, called from cache_manager.rs:276, 287.
+ */
+void copy_blocks_f16(void *key_cache_ptrs, void *value_cache_ptrs, const void *block_mapping,
+                     int64_t num_layers, int64_t num_pairs, int64_t numel_per_block,
+                     atoma_stream_t stream);
+void copy_blocks_bf16(void *key_cache_ptrs, void *value_cache_ptrs, const void *block_mapping,
+                      int64_t num_layers, int64_t num_pairs, int64_t numel_per_block,
+                      atoma_stream_t stream);
+
+/*
+ * Scatter freshly projected K/V rows into the paged caches:
+ *   key_cache[slot / block_size][slot % block_size][h][:] = key[t][h][:]   with slot = slot_mapping[t],
+ * tokens with slot < 0 are skipped.  key/value: [num_tokens, num_heads, head_size] with token
+ * stride key_stride / value_stride; caches: [num_blocks, block_size, num_heads, head_size] with
+ * block stride block_stride; dtype: 0 = f16, 1 = bf16.
+ * Replaces cache_manager.cu:140-170, 215-242, bound at ffi.rs:88-101, called from
+ * cache_manager.rs:512.
+ */
+void reshape_and_cache_flash(void *key, void *value, void *key_cache, void *value_cache,
+                             int64_t *slot_mapping, int64_t block_stride, int64_t num_tokens,
+                             int64_t num_heads, int64_t head_size, int64_t block_size,
+                             int64_t key_stride, int64_t value_stride, uint32_t dtype,
+                             atoma_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Part 2 — extensions (same semantics, B200-friendly plumbing)                                */
+/* ------------------------------------------------------------------------------------------ */
+
+/* run_mha on an explicit stream (so a decode step can be captured in a CUDA graph).  Same
+ * arguments as run_mha followed by the stream.  The reference hard-codes stream 0
+ * (flash_api.cu:157). */
+void run_mha_stream(void *q_ptr, void *k_ptr, void *v_ptr, void *o_ptr, void *softmax_lse_ptr,
+                    void *alibi_slopes_ptr, int32_t *cu_seqlens_q_ptr, int32_t *cu_seqlens_k_ptr,
+                    bool is_seqlens_k_cumulative, uint32_t q_batch_stride,
+                    uint32_t k_batch_stride, uint32_t v_batch_stride, uint32_t o_batch_stride,
+                    uint32_t alibi_slopes_batch_stride, uint32_t q_row_stride,
+                    uint32_t k_row_stride, uint32_t v_row_stride, uint32_t o_row_stride,
+                    uint32_t q_head_stride, uint32_t k_head_stride, uint32_t v_head_stride,
+                    uint32_t o_head_stride, uint32_t num_splits, uint32_t b, uint32_t h,
+                    uint32_t h_k, uint32_t d, uint32_t d_rounded, float softmax_scale,
+                    float scale_softmax_log2, int *block_table, uint32_t block_table_batch_stride,
+                    int page_block_size, int *seqused_k, uint32_t seqlen_q, uint32_t seqlen_k,
+                    uint32_t seqlen_q_rounded, uint32_t seqlen_k_rounded, int is_bf16,
+                    int is_causal, int window_size_left, int window_size_right, float softcap,
+                    bool unpadded_lse, bool force_split_kernel, void *softmax_lseaccum_ptr,
+                    void *oaccum_ptr, atoma_stream_t stream);
+
+/*
+ * Batched block swap: for p < num_pairs copy block_bytes bytes from
+ * src_base + src_blocks[p]*block_bytes to dst_base + dst_blocks[p]*block_bytes.
+ * kind: 0 = device->device (one kernel launch, 16-byte vectors; src_blocks/dst_blocks are HOST
+ * arrays, uploaded by the call), 1 = host->device, 2 = device->host (contiguous runs of blocks
+ * are coalesced into single async copies on `stream`; the host side should be pinned).
+ * Replaces the per-block memcpy loop of csrc/src/cache_manager.rs:18-128 + ops.rs:16-220, which
+ * has no C symbol in the reference.
+ */
+void swap_blocks_batched(void *dst_base, const void *src_base, const int64_t *src_blocks,
+                         const int64_t *dst_blocks, int64_t num_pairs, int64_t block_bytes,
+                         int kind, atoma_stream_t stream);
+
+/*
+ * y[T,N] = x[T,K] * w[N,K]^T, bf16 in, fp32 accumulate, bf16 out (no bias): the q/k/v/o
+ * projection of models/src/llama.rs:269-271, 311, which the reference sends to cuBLAS through
+ * candle `Linear`.  ldx/ldw/ldy are row strides in elements.
+ */
+void atoma_gemm_bf16_tn(const void *x, const void *w, void *y, int64_t T, int64_t N, int64_t K,
+                        int64_t ldx, int64_t ldw, int64_t ldy, atoma_stream_t stream);
+
+/* 0 = last call on this thread succeeded; otherwise a negative atoma code or a cudaError_t. */
+int atoma_last_status(void);
+/* Human-readable text for the last non-zero status on this thread ("" if none). */
+const char *atoma_last_error(void);
+/* Name of the kernel path the last run_mha on this thread dispatched to (for tests/bench). */
+const char *atoma_last_mha_path(void);
+/* Number of kernels launched by this library on this thread since the last reset. */
+int64_t atoma_launch_count(void);
+void atoma_reset_launch_count(void);
+/* Library version string. */
+const char *atoma_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATOMA_FLASH_H_ */

@@ -1,0 +1,78 @@
+"""The C-ABI library loads and exports every symbol include/*.h declares (no compute calls: this
+runs without a GPU).  Also checks that the four reference symbols (csrc/src/ffi.rs:4-101) are there
+under their exact names, and that the static archive the Rust build links exists."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from atoma_infer_b200 import _lib
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADERS = [ROOT / "include" / "atoma_flash.h", ROOT / "include" / "atoma_ops.h"]
+REFERENCE_SYMBOLS = ["run_mha", "copy_blocks_f16", "copy_blocks_bf16", "reshape_and_cache_flash"]
+
+
+def declared_functions():
+    names = []
+    for h in HEADERS:
+        src = re.sub(r"/\*.*?\*/", "", h.read_text(), flags=re.S)
+        src = re.sub(r"//[^\n]*", "", src)
+        src = re.sub(r"^\s*#[^\n]*", "", src, flags=re.M)
+        src = re.sub(r"typedef\s+struct\s+\w+\s*\{.*?\}\s*\w+\s*;", "", src, flags=re.S)
+        for m in re.finditer(r"\b([A-Za-z_]\w*)\s*\(([^;{}]*)\)\s*;", src):
+            names.append(m.group(1))
+    return sorted(set(names))
+
+
+def test_headers_declare_the_reference_abi():
+    names = declared_functions()
+    for s in REFERENCE_SYMBOLS:
+        assert s in names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = C.CDLL(str(_lib.LIB_PATH))
+    names = declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ but not exported by {_lib.LIB_PATH.name}"
+
+
+def test_python_binding_covers_every_declared_symbol():
+    assert sorted(_lib.SIGNATURES) == declared_functions()
+
+
+def test_run_mha_signature_has_the_reference_arity():
+    # csrc/src/ffi.rs:4-66 lists 47 parameters
+    assert len(_lib.SIGNATURES["run_mha"][1]) == 47
+    assert len(_lib.SIGNATURES["run_mha_stream"][1]) == 48
+    assert len(_lib.SIGNATURES["reshape_and_cache_flash"][1]) == 14
+    assert len(_lib.SIGNATURES["copy_blocks_bf16"][1]) == 7
+
+
+def test_static_archive_for_the_rust_link_line():
+    # csrc/build.rs:104-113 links `static=flashattention`
+    a = _lib.LIB_PATH.with_name("libflashattention.a")
+    assert a.exists()
+    out = subprocess.run(["nm", "-g", "--defined-only", str(a)], capture_output=True, text=True).stdout
+    for s in REFERENCE_SYMBOLS:
+        assert re.search(rf"\bT {s}\b", out), s
+
+
+def test_version_and_status_calls_work_without_a_gpu():
+    L = _lib.lib()
+    assert b"sm_100a" in L.atoma_version()
+    assert L.atoma_last_status() == 0
+    assert L.atoma_launch_count() >= 0
+
+
+def test_sass_is_blackwell_native():
+    """The decode kernel must carry TMA (UTMALDG) and the library must be built for sm_100a."""
+    out = subprocess.run(["cuobjdump", "-lelf", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["cuobjdump", "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "UTMALDG" in sass, "no TMA tensor loads in the library SASS"
+    assert "UBLKCP" in sass, "no bulk async copies (copy_blocks) in the library SASS"
