@@ -1,0 +1,482 @@
+#!/usr/bin/env python
+"""Benchmark of the attention hot path at BASELINE.json's headline configuration.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config 2 of BASELINE.json): one DECODE STEP of Llama-3.1-8B's attention path, bf16,
+batch 32, every sequence at context 4096, block_size 16 — for each of the 32 layers
+
+    qkv = x . Wqkv^T            (models/src/llama.rs:269-271; one fused-N GEMM)
+    reshape_and_cache_flash     (models/src/flash_attention.rs:361)
+    paged decode attention      (flash_attention.rs:455 -> flash_attn_kv_cache_full -> run_mha)
+    x = attn . Wo^T             (llama.rs:311)  [+ NCCL all-reduce under tensor parallelism]
+
+with a distinct 541 MB KV cache per layer (17.3 GB in total: every layer's K/V comes from HBM, no
+L2 flush needed).  RoPE, MLP, norms and lm_head are outside SURVEY §8's scope table and not timed;
+`config.workload` says so.  Metric: decode tokens/s = batch / step time, whole job.
+
+`--impl ours` runs libflashattention (this repo's sm_100a kernels) through the public operator API
+(atoma_infer_b200.ops); `--impl reference` runs the REFERENCE's own kernels (oracle/_ref, compiled
+from /root/reference/csrc/kernels for sm_100) with the argument tuples its Rust wrappers derive,
+launched eagerly from one host thread on the legacy default stream as the reference does.  The
+reference has no CPU implementation of this path (cpu_fwd bails, csrc/src/lib.rs:1862-1872): its
+"CPU-host-timed" number is host wall-clock around the GPU step, which is what that arm reports.
+Dense GEMMs are cuBLAS (torch.matmul) in the reference arm, as in the reference (candle -> cuBLAS).
+
+N > 1: tensor parallel over heads exactly like the reference (models/src/llama_nccl.rs:164-171):
+each rank holds H/N query heads, Hkv/N kv heads, its slice of every KV cache and of Wqkv / Wo, and
+all-reduces the o_proj output with NCCL.  Total work is fixed -> "scaling": "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+# Llama-3.1-8B attention geometry
+L, HIDDEN, H, HK, D, PAGE = 32, 4096, 32, 8, 128, 16
+BATCH, CTX = 32, 4096
+MB = CTX // PAGE  # block-table width
+METRIC = "decode tokens/sec Llama-3.1-8B bf16 b32 ctx4k (attention path: qkv_proj + cache write + paged decode attention + o_proj, 32 layers)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layers", type=int, default=L, help="debug only; the reported config needs 32")
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--gemm", default="auto", choices=["auto", "atoma", "cublas"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks (B200_PROFILING.md: sample nvidia-smi DURING the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.proc, self.path, self.dev = None, None, device_index
+        if shutil.which("nvidia-smi"):
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(device_index)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower() == "active":
+                    reasons.add(n)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        # "under load": the upper half of the samples (the sampler also sees the idle edges)
+        load = sm[len(sm) // 2:]
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# state
+# ------------------------------------------------------------------------------------------------
+class State:
+    """Per-rank synthetic model slice + KV caches + step metadata, all seeded."""
+
+    def __init__(self, torch, rank: int, world: int, layers: int, dev):
+        self.torch, self.rank, self.world, self.layers, self.dev = torch, rank, world, layers, dev
+        self.h, self.hk = H // world, HK // world
+        self.nb = BATCH * MB + 64
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        bf = torch.bfloat16
+        nq, nkv = self.h * D, self.hk * D
+        self.wqkv = [(torch.randn((nq + 2 * nkv, HIDDEN), generator=g, device=dev, dtype=torch.float32)
+                      * HIDDEN ** -0.5).to(bf) for _ in range(layers)]
+        self.wo = [(torch.randn((HIDDEN, nq), generator=g, device=dev, dtype=torch.float32)
+                    * (H * D) ** -0.5).to(bf) for _ in range(layers)]
+        self.kv = []
+        for _ in range(layers):
+            c = torch.empty((2, self.nb, PAGE, self.hk, D), device=dev, dtype=bf)
+            c.normal_(generator=g)
+            self.kv.append(c)
+        # metadata is identical on every rank (same scheduler output broadcast, model_executor.rs:531-542)
+        gm = torch.Generator(device="cpu").manual_seed(99)
+        perm = torch.randperm(self.nb, generator=gm)[: BATCH * MB].to(torch.int32).reshape(BATCH, MB)
+        lens = torch.full((BATCH,), CTX, dtype=torch.int32)
+        last = (lens.long() - 1)
+        slots = perm[torch.arange(BATCH), (last // PAGE)].long() * PAGE + last % PAGE  # worker.rs:392-401
+        x = (torch.randn((BATCH, HIDDEN), generator=gm, dtype=torch.float32)).to(bf)
+        # pinned host copies (the step's inputs) and their device images
+        self.host = {"x": x.pin_memory(), "bt": perm.pin_memory(), "lens": lens.pin_memory(),
+                     "slots": slots.pin_memory()}
+        self.devt = {k: v.to(dev) for k, v in self.host.items()}
+        self.out = torch.empty((BATCH, HIDDEN), device=dev, dtype=bf)
+        self.out_host = torch.empty((BATCH, HIDDEN), dtype=bf).pin_memory()
+        self.scale = D ** -0.5
+
+    def h2d_bytes(self):
+        return sum(t.numel() * t.element_size() for t in self.host.values())
+
+    def d2h_bytes(self):
+        return self.out_host.numel() * self.out_host.element_size()
+
+    def upload(self):
+        for k, v in self.host.items():
+            self.devt[k].copy_(v, non_blocking=True)
+
+    def download(self):
+        self.out_host.copy_(self.out, non_blocking=True)
+
+
+def make_step(st: State, impl: str, gemm: str, dist):
+    """Returns step() -> None that runs all layers on the current stream and leaves the result in
+    st.out."""
+    torch = st.torch
+    nq, nkv = st.h * D, st.hk * D
+    d = st.devt
+
+    if impl == "ours":
+        from atoma_infer_b200 import ops
+
+        def mm(a, w):
+            if gemm == "atoma":
+                return ops.gemm_bf16_tn(a, w)
+            return torch.matmul(a, w.t())
+
+        def attn(q, kc, vc, layer):
+            return ops.flash_attn_kv_cache_full(q, kc, vc, None, st.scale, d["bt"], d["lens"], True)
+
+        def cache_write(k, v, kc, vc):
+            ops.reshape_and_cache_flash(k, v, kc, vc, d["slots"])
+    else:
+        from atoma_infer_b200 import ops  # host planner only: derives the reference's run_mha arguments
+        from oracle.ref_lib import RefLib
+        ref = RefLib()
+        sms = torch.cuda.get_device_properties(st.dev).multi_processor_count
+        stream0 = 0  # legacy default stream, like the reference (flash_api.cu:157)
+
+        def mm(a, w):
+            return torch.matmul(a, w.t())
+
+        def attn(q, kc, vc, layer):
+            plan = ops.flash_attn_kv_cache_plan(q, kc, vc, st.scale, block_table=d["bt"], seqlens_k=d["lens"],
+                                                window_size_right=0, num_sms=sms)
+            return ref.execute(plan, q, sync=False)
+
+        def cache_write(k, v, kc, vc):
+            ref.lib.reshape_and_cache_flash(k.data_ptr(), v.data_ptr(), kc.data_ptr(), vc.data_ptr(),
+                                            d["slots"].data_ptr(), kc.stride(0), BATCH, st.hk, D, PAGE,
+                                            k.stride(0), v.stride(0), 1, stream0)
+
+    def step():
+        x = d["x"]
+        for l in range(st.layers):
+            qkv = mm(x, st.wqkv[l])                                   # [B, (h + 2 hk) D]
+            q = qkv[:, :nq].unflatten(1, (st.h, D)).unsqueeze(1)      # [B, 1, h, D] (strided view)
+            k = qkv[:, nq:nq + nkv].unflatten(1, (st.hk, D))          # [B, hk, D]
+            v = qkv[:, nq + nkv:].unflatten(1, (st.hk, D))
+            kc, vc = st.kv[l][0], st.kv[l][1]
+            cache_write(k, v, kc, vc)
+            o = attn(q, kc, vc, l)                                    # [B, 1, h, D]
+            x = mm(o.reshape(BATCH, nq), st.wo[l])                    # [B, hidden]
+            if st.world > 1:
+                dist.all_reduce(x)                                    # multi_gpu.rs:141-179
+        st.out.copy_(x)
+
+    return step
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the numpy oracle ("port") on a bounded sample of the same workload
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(seconds_budget: float = 20.0):
+    import numpy as np
+    from oracle import attention_oracle as orc
+    rng = np.random.default_rng(0)
+    b, mb = 2, MB
+    nb = b * mb
+    f = lambda *s: orc.round_to_io(rng.standard_normal(s, dtype=np.float32), True)
+    kc, vc = f(nb, PAGE, HK, D), f(nb, PAGE, HK, D)
+    x = f(b, HIDDEN)
+    wqkv, wo = f((H + 2 * HK) * D, HIDDEN) * HIDDEN ** -0.5, f(HIDDEN, H * D) * (H * D) ** -0.5
+    bt = rng.permutation(nb).astype(np.int32).reshape(b, mb)
+    lens = np.full(b, CTX)
+    slots = bt[np.arange(b), (lens - 1) // PAGE].astype(np.int64) * PAGE + (lens - 1) % PAGE
+    kcb, vcb = orc.from_f32(kc, True).ravel(), orc.from_f32(vc, True).ravel()   # flat storage bits
+    t0 = time.perf_counter()
+    n = 0
+    while True:  # one "layer" of the path for b sequences
+        qkv = orc.round_to_io((x @ wqkv.T).astype(np.float32), True)
+        nq, nkv = H * D, HK * D
+        q = np.ascontiguousarray(qkv[:, :nq]).reshape(b, 1, H, D)
+        orc.reshape_and_cache_flash(orc.from_f32(qkv, True).ravel()[nq:], orc.from_f32(qkv, True).ravel()[nq + nkv:],
+                                    kcb, vcb, slots, PAGE * nkv, b, HK, D, PAGE, qkv.shape[1], qkv.shape[1])
+        o, _ = orc.attention_paged_decode(q, orc.to_f32(kcb, True).reshape(kc.shape), orc.to_f32(vcb, True).reshape(vc.shape),
+                                          bt, lens, D ** -0.5, True, precision="reference")
+        x2 = orc.round_to_io((o.reshape(b, nq) @ wo.T).astype(np.float32), True)
+        n += 1
+        if time.perf_counter() - t0 > seconds_budget or n >= 8:
+            break
+    dt = (time.perf_counter() - t0) / n            # seconds per layer for b sequences
+    tok_s = b / (dt * L)
+    del x2
+    return {"value": tok_s, "unit": "tokens/s", "cores": 1, "kind": "port",
+            "sample": f"numpy oracle (oracle/attention_oracle.py), {n} layer pass(es) of the same path for {b} of "
+                      f"the 32 sequences at ctx {CTX}; scaled to 32 layers"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != max(1, args.gpus) and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.impl == "reference" and rank != 0:
+        return  # rank 0 alone runs the reference arm
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU or PyTorch fallback for the product path)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    tp = world if args.impl == "ours" else 1
+    if world > 1 and args.impl == "ours":
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if HK % tp != 0:
+        raise SystemExit(f"tensor parallel degree {tp} must divide the {HK} kv heads")
+
+    from atoma_infer_b200 import _lib, ops
+    _lib.lib()  # fail loudly if libflashattention.so is missing
+    if args.impl == "reference":
+        from oracle.ref_lib import RefLib
+        if not RefLib.available():
+            raise SystemExit("oracle/_ref/libatoma_ref.so is missing: run __graft_entry__.build() where /root/reference exists")
+
+    gemm = args.gemm
+    if gemm == "auto":
+        gemm = "cublas"
+        if args.impl == "ours":
+            # use the hand-written GEMM once it is built (the placeholder reports "unsupported")
+            try:
+                a = torch.zeros((BATCH, 64), device=dev, dtype=torch.bfloat16)
+                w = torch.zeros((128, 64), device=dev, dtype=torch.bfloat16)
+                ops.gemm_bf16_tn(a, w)
+                gemm = "atoma"
+            except Exception:
+                gemm = "cublas"
+
+    st = State(torch, rank if args.impl == "ours" else 0, tp, args.layers, dev)
+    step = make_step(st, args.impl, gemm, dist)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- one eager step: allocates library workspaces, warms cuBLAS; then capture ----
+    ops.reset_launch_count()
+    step()
+    torch.cuda.synchronize()
+    launches_per_step = ops.launch_count() if args.impl == "ours" else 0
+    use_graph = args.impl == "ours" and not args.no_graph
+    graph = None
+    if use_graph:
+        try:
+            # The library keeps one workspace per (device, stream) and refuses to allocate during
+            # capture: run one eager step on the capture stream first.
+            side = torch.cuda.Stream()
+            side.wait_stream(stream)
+            with torch.cuda.stream(side):
+                step()
+            stream.wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                step()
+            torch.cuda.synchronize()
+        except Exception as e:  # pragma: no cover - depends on the box
+            print(f"[bench] CUDA graph capture failed ({e}); launching eagerly", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+    run = graph.replay if graph is not None else step
+
+    for _ in range(max(args.warmup, 3)):
+        run()
+    barrier()
+
+    # ---- timed region 1: device-resident inputs, K steps, CUDA events ----
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        run()
+    e1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    ms_dev = e0.elapsed_time(e1)
+
+    # ---- timed region 2 (e2e): host buffers -> H2D -> step -> D2H, every step ----
+    for _ in range(2):
+        st.upload(); run(); st.download()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e2.record()
+    for _ in range(args.steps):
+        st.upload()
+        run()
+        st.download()
+        stream.synchronize()  # the step's result is on the host before the next step starts
+    e3.record()
+    barrier()
+    t_e2e_wall = time.perf_counter() - t0
+    ms_e2e = max(e2.elapsed_time(e3), t_e2e_wall * 1e3)  # host wall-clock includes the syncs
+    clocks = sampler.stop() if sampler else None
+
+    # ---- dominant kernel alone: paged decode attention, one launch per layer (distinct caches) ----
+    nq = st.h * D
+    qs = torch.randn((BATCH, 1, st.h, D), device=dev, dtype=torch.float32).to(torch.bfloat16)
+    if args.impl == "ours":
+        def attn_only(l):
+            return ops.flash_attn_kv_cache_full(qs, st.kv[l][0], st.kv[l][1], None, st.scale, st.devt["bt"],
+                                                st.devt["lens"], True)
+    else:
+        from oracle.ref_lib import RefLib
+        ref = RefLib()
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+
+        def attn_only(l):
+            plan = ops.flash_attn_kv_cache_plan(qs, st.kv[l][0], st.kv[l][1], st.scale, block_table=st.devt["bt"],
+                                                seqlens_k=st.devt["lens"], window_size_right=0, num_sms=sms)
+            return ref.execute(plan, qs, sync=False)
+    for l in range(st.layers):
+        attn_only(l)
+    torch.cuda.synchronize()
+    reps = 3
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(reps):
+        for l in range(st.layers):
+            attn_only(l)
+    k1.record()
+    torch.cuda.synchronize()
+    us_kernel = k0.elapsed_time(k1) * 1e3 / (reps * st.layers)
+
+    # ---- max over ranks ----
+    times = torch.tensor([ms_dev, ms_e2e, us_kernel], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e, us_kernel = [float(x) for x in times.tolist()]
+
+    if rank == 0:
+        peaks = {}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
+        # ALGORITHMIC bytes of one decode-attention launch: K and V of every cached token
+        # once + q and o + the block table, per rank.
+        kv_bytes = 2 * BATCH * CTX * st.hk * D * 2
+        alg_bytes = kv_bytes + 2 * BATCH * st.h * D * 2 + BATCH * MB * 4
+        achieved = alg_bytes / (us_kernel * 1e-6) / 1e9
+        ms_step = ms_dev / args.steps
+        ms_step_e2e = ms_e2e / args.steps
+        line = {
+            "metric": METRIC,
+            "value": BATCH / (ms_step * 1e-3),
+            "unit": "tokens/s",
+            "n_gpus": world if args.impl == "ours" else 1,
+            "steps": args.steps,
+            "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step,
+            "higher_is_better": True,
+            "scaling": "strong",
+            "vs_baseline": None,
+            "dtype": "bf16",
+            "data": "synthetic (seeded N(0,1) activations / KV caches, random-init weights, random block tables)",
+            "config": {
+                "workload": f"BASELINE.json configs[1]: Llama-3.1-8B bf16 batch=32 ctx=4096 decode-only, block_size=16; "
+                            f"attention path of one decode step ({st.layers} layers x [fused qkv GEMM, reshape_and_cache_flash, "
+                            f"paged decode attention, o_proj GEMM]); RoPE/MLP/norms/lm_head not in SURVEY §8 scope and not timed",
+                "batch": BATCH, "ctx": CTX, "layers": st.layers, "heads": H, "kv_heads": HK, "head_dim": D,
+                "block_size": PAGE, "parallelism": f"tp{tp}",
+                "l2": "inputs larger than L2: 541 MB of KV per layer, 17.3 GB per step, distinct per layer",
+                "launch": "cuda graph replay" if graph is not None else "eager, one host thread",
+                "gemm": "atoma tcgen05 kernel" if gemm == "atoma" else "cuBLAS via torch.matmul (library GEMM, as in the reference)",
+                "wall_ms_per_step": t_wall * 1e3 / args.steps,
+            },
+            "e2e": {"value": BATCH / (ms_step_e2e * 1e-3), "unit": "tokens/s",
+                    "h2d_bytes_per_step": st.h2d_bytes(), "d2h_bytes_per_step": st.d2h_bytes(),
+                    "ms_per_step": ms_step_e2e},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "decode_paged_kernel" if args.impl == "ours" else "flash_fwd_splitkv_kernel",
+                         "achieved": achieved, "peak": peak_hbm, "unit": "GB/s", "frac": achieved / peak_hbm,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                         "us_per_launch": us_kernel, "algorithmic_bytes_per_launch": alg_bytes,
+                         "frac_of_8TBps": achieved / 8000.0, "traffic": None},
+        }
+        if args.impl == "reference":
+            line["impl"] = "reference"
+            line["value"] = line["e2e"]["value"]   # the reference's number is host-timed by definition
+            line["ms_per_step"] = ms_step_e2e
+            line["e2e"] = {"value": line["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+            line["config"]["device_ms_per_step"] = ms_step
+            line["cpu_baseline"] = {
+                "value": line["value"], "unit": "tokens/s", "cores": 1, "kind": "reference",
+                "sample": "the reference's own CUDA kernels (oracle/_ref, built from /root/reference/csrc/kernels for sm_100) "
+                          "driven from ONE host thread with host wall-clock timing, as the reference times itself "
+                          "(model_executor.rs:331-347); the reference has no CPU implementation of this path"}
+        elif not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -138,8 +138,10 @@ def _kv_row_offsets(a: MhaArgs, bidb: int, len_k: int, seq_off: int, batch_strid
     return seq_off + t * row_stride
 
 
-def run_mha(a: MhaArgs, precision: str = "fp64"):
-    """Returns (o_bits uint16 flat [o_size], lse float32 [b, h, seqlen_q]).
+def run_mha(a: MhaArgs, precision: str = "fp64", return_exact: bool = False):
+    """Returns (o_bits uint16 flat [o_size], lse float32 [b, h, seqlen_q]) and, with
+    return_exact, also the un-rounded output as float64 flat [o_size] (what the 16-bit result is a
+    rounding of — the tests bound |kernel - exact| by the output format's half-ulp plus 1e-3).
 
     precision="fp64": exact math in float64, one rounding at the output (the specification).
     precision="reference": fp32 scores/softmax, P rounded to the io type before P.V, fp32
@@ -149,6 +151,7 @@ def run_mha(a: MhaArgs, precision: str = "fp64"):
     assert precision in ("fp64", "reference")
     ft = np.float64 if precision == "fp64" else np.float32
     o = np.zeros(a.o_size, dtype=np.uint16)
+    o_exact = np.zeros(a.o_size, dtype=np.float64)
     lse = np.full((a.b, a.h, a.seqlen_q), np.inf, dtype=np.float32)
     ratio = a.h // a.h_k
     dcol = np.arange(a.d, dtype=np.int64)
@@ -190,9 +193,12 @@ def run_mha(a: MhaArgs, precision: str = "fp64"):
             acc = p @ vm
             inv = np.where((l == 0) | np.isnan(l), 1.0, 1.0 / np.where(l == 0, 1.0, l))
             o[oi] = from_f32((acc * inv).astype(np.float32), a.is_bf16)
+            o_exact[oi] = acc * inv
             with np.errstate(divide="ignore"):
                 row_lse = np.where((l == 0) | np.isnan(l), np.inf, m_safe + np.log(np.where(l == 0, 1.0, l)))
             lse[bidb, head, :len_q] = row_lse[:, 0].astype(np.float32)
+    if return_exact:
+        return o, lse, o_exact
     return o, lse
 
 
@@ -235,7 +241,7 @@ def swap_blocks(src: np.ndarray, dst: np.ndarray, block_mapping: dict, block_num
 # Shape-level conveniences used by the tests
 # ------------------------------------------------------------------------------------------------
 def attention_dense(q: np.ndarray, k: np.ndarray, v: np.ndarray, scale: float, causal: bool,
-                    is_bf16: bool, precision: str = "fp64", alibi=None):
+                    is_bf16: bool, precision: str = "fp64", alibi=None, exact: bool = False):
     """q [b,sq,h,d], k/v [b,sk,hk,d] float32 (already representable in the io type)."""
     b, sq, h, d = q.shape
     _, sk, hk, _ = k.shape
@@ -246,12 +252,15 @@ def attention_dense(q: np.ndarray, k: np.ndarray, v: np.ndarray, scale: float, c
                 o_row_stride=h * d, q_head_stride=d, k_head_stride=d, v_head_stride=d, o_head_stride=d,
                 softmax_scale=scale, is_bf16=is_bf16, is_causal=causal, alibi_slopes=alibi,
                 o_size=b * sq * h * d)
-    o, lse = run_mha(a, precision)
+    o, lse, ox = run_mha(a, precision, return_exact=True)
+    if exact:
+        return ox.reshape(b, sq, h, d), lse
     return to_f32(o, is_bf16).reshape(b, sq, h, d), lse
 
 
 def attention_paged_decode(q: np.ndarray, k_cache: np.ndarray, v_cache: np.ndarray, block_table: np.ndarray,
-                           seqlens_k: np.ndarray, scale: float, is_bf16: bool, precision: str = "fp64"):
+                           seqlens_k: np.ndarray, scale: float, is_bf16: bool, precision: str = "fp64",
+                           exact: bool = False):
     """q [b,1,h,d]; caches [nb,page,hk,d]; block_table [b,mb]; seqlens_k [b] (per-sequence)."""
     b, sq, h, d = q.shape
     nb, page, hk, _ = k_cache.shape
@@ -265,5 +274,7 @@ def attention_paged_decode(q: np.ndarray, k_cache: np.ndarray, v_cache: np.ndarr
                 cu_seqlens_k=seqlens_k.astype(np.int32), is_seqlens_k_cumulative=False,
                 block_table=block_table.astype(np.int32).ravel(), block_table_batch_stride=mb,
                 page_block_size=page, o_size=b * sq * h * d)
-    o, lse = run_mha(a, precision)
+    o, lse, ox = run_mha(a, precision, return_exact=True)
+    if exact:
+        return ox.reshape(b, sq, h, d), lse
     return to_f32(o, is_bf16).reshape(b, sq, h, d), lse

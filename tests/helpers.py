@@ -11,7 +11,6 @@ import torch
 
 ROOT = Path(__file__).resolve().parent.parent
 GOLDEN = json.loads((ROOT / "tests" / "golden" / "attention_tables.json").read_text())
-REF_SO = ROOT / "oracle" / "_ref" / "libatoma_ref.so"
 
 
 def golden_inputs_np():
@@ -78,69 +77,86 @@ def ulp16(x: np.ndarray, is_bf16: bool) -> np.ndarray:
     return 2.0 ** (e - mant)
 
 
-def assert_close_16(actual: np.ndarray, expected64: np.ndarray, is_bf16: bool, what: str,
-                    norm_tol: float = 1e-3, ulps: float = 1.0, atol: float = 2e-3):
-    """The parity bar: norm-wise relative error <= 1e-3 (the north star's
-    tolerance) AND every element within `ulps` units in the last place of the 16-bit type (+ a small
-    absolute floor for outputs near zero, where cancellation dominates)."""
+def quant_floor(expected64: np.ndarray, is_bf16: bool) -> float:
+    """Norm-wise relative error of the CORRECTLY ROUNDED 16-bit image of `expected64`: the error any
+    implementation with a 16-bit output carries (about 1.6e-3 for bf16, 2e-4 for f16)."""
+    from oracle import attention_oracle as orc
+    x = np.asarray(expected64, dtype=np.float64)
+    r = orc.round_to_io(x.astype(np.float32), is_bf16).astype(np.float64)
+    return rel_err(r, x)
+
+
+# Half-ulp of the 16-bit io type: the relative error of every P element, which the reference
+# rounds to the io type before P.V (flash_fwd_kernel.h:949-954) and so do we.
+EPS_P = {True: 2.0 ** -9, False: 2.0 ** -12}
+
+
+def p_noise(exact64: np.ndarray, is_bf16: bool, sigmas: float = 8.0) -> np.ndarray:
+    """Per-element allowance for the rounding of P before P.V.  The error of one output element is
+    sum_t p_t e_t v_t / sum_t p_t with independent |e_t| <= EPS_P: standard deviation
+    EPS_P / sqrt(3) * sqrt(sum p_t^2 v_t^2) / sum p_t, i.e. EPS_P / sqrt(3) times the typical
+    magnitude of an output element of that row.  `sigmas` of it, with the row's rms as the typical
+    magnitude (rows = last axis); 8 sigma because the tests compare up to 5e6 elements and the row rms
+    is itself an estimate from D samples."""
+    x = np.asarray(exact64, dtype=np.float64)
+    rms = np.sqrt(np.mean(x ** 2, axis=-1, keepdims=True)) if x.size else x
+    return sigmas * EPS_P[is_bf16] / np.sqrt(3.0) * np.broadcast_to(rms, x.shape)
+
+
+def _worst(diff, bound, ref):
+    i = np.unravel_index(int(np.argmax(diff - bound)), diff.shape)
+    return f"worst excess {(diff - bound)[i]:.3e} at index {i} where |exact|={abs(ref[i]):.3e}, diff={diff[i]:.3e}"
+
+
+def assert_close_16(actual: np.ndarray, exact64: np.ndarray, is_bf16: bool, what: str,
+                    tol: float = 1e-3, atol: float = 1e-5):
+    """The parity bar against the fp64 oracle (DESIGN.md "Parity"): the north star's 1e-3 relative
+    tolerance on top of the two roundings that the reference's algorithm itself performs and that no
+    16-bit implementation of it avoids — the output format's and P's:
+
+      norm-wise     ||out - exact|| / ||exact|| <= tol + quant_floor(exact)
+      element-wise  |out - exact| <= tol * |exact| + 0.5 ulp_16(exact) + p_noise(exact) + atol
+
+    `exact64` is the un-rounded fp64 oracle output."""
     actual = np.asarray(actual, dtype=np.float64)
-    expected64 = np.asarray(expected64, dtype=np.float64)
-    assert actual.shape == expected64.shape, (what, actual.shape, expected64.shape)
+    exact64 = np.asarray(exact64, dtype=np.float64)
+    assert actual.shape == exact64.shape, (what, actual.shape, exact64.shape)
     assert np.isfinite(actual).all(), f"{what}: non-finite output"
-    r = rel_err(actual, expected64)
-    assert r <= norm_tol, f"{what}: norm-wise rel err {r:.3e} > {norm_tol}"
-    bound = ulps * ulp16(expected64, is_bf16) + atol * np.maximum(1e-3, np.abs(expected64).max()) * 1e-1
-    bad = np.abs(actual - expected64) > bound
-    assert not bad.any(), (f"{what}: {bad.sum()} / {bad.size} elements beyond {ulps} ulp; "
-                           f"max abs diff {np.abs(actual - expected64).max():.3e}")
+    r, floor = rel_err(actual, exact64), quant_floor(exact64, is_bf16)
+    assert r <= tol + floor, f"{what}: norm-wise rel err {r:.3e} > {tol} + quantisation floor {floor:.3e}"
+    bound = tol * np.abs(exact64) + 0.5 * ulp16(exact64, is_bf16) + p_noise(exact64, is_bf16) + atol
+    diff = np.abs(actual - exact64)
+    bad = diff > bound
+    assert not bad.any(), f"{what}: {bad.sum()} / {bad.size} elements beyond tol; {_worst(diff, bound, exact64)}"
+    return r, floor
 
 
-# ------------------------------------------------------------------------------------------------
+def assert_same_up_to_rounding(a: np.ndarray, b: np.ndarray, exact64: np.ndarray, is_bf16: bool, what: str,
+                               tol: float = 1e-3, slack: float = 1.10):
+    """Two 16-bit implementations of the same fp32 algorithm (ours = a, the reference's kernels = b)
+    that differ in tile order and split policy, hence in every rounding:
+
+      norm-wise     ||a - b|| / ||b|| <= tol + sqrt(2) * quant_floor        (two output roundings)
+      element-wise  |a - b| <= tol * |b| + 1 ulp_16 + sqrt(2) * p_noise     (two roundings of P each)
+      accuracy      ours is no further from the exact result than the reference is (within `slack`)"""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    exact64 = np.asarray(exact64, dtype=np.float64)
+    assert np.isfinite(a).all(), f"{what}: non-finite output"
+    r, floor = rel_err(a, b), quant_floor(exact64, is_bf16)
+    assert r <= tol + np.sqrt(2.0) * floor, f"{what}: norm-wise rel diff {r:.3e} vs the reference kernels"
+    bound = (tol * np.abs(b) + ulp16(np.maximum(np.abs(a), np.abs(b)), is_bf16) +
+             np.sqrt(2.0) * p_noise(exact64, is_bf16) + 1e-5)
+    diff = np.abs(a - b)
+    bad = diff > bound
+    assert not bad.any(), f"{what}: {bad.sum()} / {bad.size} elements apart; {_worst(diff, bound, exact64)}"
+    ra, rb = rel_err(a, exact64), rel_err(b, exact64)
+    assert ra <= slack * rb + 1e-4, f"{what}: ours {ra:.3e} vs reference {rb:.3e} from the exact result"
+    return ra, rb
+
+
 # The reference's own kernels (compiled from /root/reference into oracle/_ref by oracle/ref_build)
-# ------------------------------------------------------------------------------------------------
-class RefLib:
-    def __init__(self):
-        from atoma_infer_b200 import _lib
-        self.lib = C.CDLL(str(REF_SO), mode=C.RTLD_LOCAL)
-        self.lib.run_mha.restype = None
-        self.lib.run_mha.argtypes = _lib.SIGNATURES["run_mha"][1]
-        for n in ("copy_blocks_f16", "copy_blocks_bf16", "reshape_and_cache_flash"):
-            getattr(self.lib, n).restype = None
-            getattr(self.lib, n).argtypes = _lib.SIGNATURES[n][1]
-
-    @staticmethod
-    def available() -> bool:
-        return REF_SO.exists()
-
-    def run_mha_plan(self, plan, out: torch.Tensor, lse: torch.Tensor, lseaccum=None, oaccum=None):
-        """Call the reference run_mha with the argument tuple of a plan (legacy stream 0)."""
-        a = plan.args
-        torch.cuda.synchronize()
-        self.lib.run_mha(
-            a.q_ptr, a.k_ptr, a.v_ptr, out.data_ptr(), lse.data_ptr(), a.alibi_slopes_ptr,
-            a.cu_seqlens_q_ptr, a.cu_seqlens_k_ptr, a.is_seqlens_k_cumulative,
-            a.q_batch_stride, a.k_batch_stride, a.v_batch_stride, a.o_batch_stride, a.alibi_slopes_batch_stride,
-            a.q_row_stride, a.k_row_stride, a.v_row_stride, a.o_row_stride,
-            a.q_head_stride, a.k_head_stride, a.v_head_stride, a.o_head_stride,
-            a.num_splits, a.b, a.h, a.h_k, a.d, a.d_rounded, a.softmax_scale, a.scale_softmax_log2,
-            a.block_table, a.block_table_batch_stride, a.page_block_size, a.seqused_k,
-            a.seqlen_q, a.seqlen_k, a.seqlen_q_rounded, a.seqlen_k_rounded, a.is_bf16, a.is_causal,
-            a.window_size_left, a.window_size_right, a.softcap, a.unpadded_lse, a.force_split_kernel,
-            lseaccum.data_ptr() if lseaccum is not None else None,
-            oaccum.data_ptr() if oaccum is not None else None)
-        torch.cuda.synchronize()
-
-    def execute(self, plan, like: torch.Tensor) -> torch.Tensor:
-        """Allocate what the Rust wrapper allocates (csrc/src/lib.rs:1726-1729, 1785-1800) and run."""
-        shape = [plan.out_shape[i] for i in range(plan.out_rank)]
-        out = torch.empty(shape, dtype=like.dtype, device=like.device)
-        lse = torch.zeros(max(int(plan.lse_elems), 1), dtype=torch.float32, device=like.device)
-        lacc = oacc = None
-        if plan.args.num_splits > 1:
-            lacc = torch.zeros(int(plan.lseaccum_elems), dtype=torch.float32, device=like.device)
-            oacc = torch.zeros(int(plan.oaccum_elems), dtype=torch.float32, device=like.device)
-        self.run_mha_plan(plan, out, lse, lacc, oacc)
-        return out
+from oracle.ref_lib import REF_SO, RefLib  # noqa: E402,F401
 
 
 def make_paged_cache(num_blocks, page, hk, d, dtype, device, seed, poison_unused=False):
