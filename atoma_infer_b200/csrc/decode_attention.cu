@@ -41,6 +41,8 @@ constexpr int kStageRows = 128;                        // (token, head) rows per
 constexpr int kMaxBatch = 2047;
 constexpr int kMaxCounters = 16384;                    // B * head groups
 constexpr int kPartRows = 16;                          // M of the mma tile
+constexpr int kMaxCtas = 256;                          // persistent grid size limit
+constexpr int kCombineBatch = 8;                       // sub-partials loaded per combine step
 
 template <int D>
 struct Cfg {
@@ -62,7 +64,19 @@ struct DecodeArgs {
     int *counters;   // [b * hg], zero between launches
     float *ws_ml;    // [cta][2][8 warps][16 rows][2]
     float *ws_o;     // [cta][2][8 warps][16 rows][D]
+    unsigned long long *trace;  // diagnostics (atoma_debug_decode_trace): [cta][4] or null
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned sm_id() {
+    unsigned v;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
+    return v;
+}
 
 __device__ __forceinline__ int seq_len_k(const MhaParams &p, int b) {
     int len;
@@ -92,9 +106,16 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
     __shared__ __align__(8) uint64_t full_k[C::kStages], full_v[C::kStages], empty[C::kStages];
     __shared__ int cum[kMaxBatch + 2];  // cum[b] = first unit of sequence b
     __shared__ int combine_flag;
+    __shared__ int part_base[kMaxCtas];  // combine: workspace index of each contributing CTA's partial
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int B = p.b;
+    if (a.trace && tid == 0) {
+        a.trace[blockIdx.x * 4 + 0] = sm_id();
+        a.trace[blockIdx.x * 4 + 1] = global_timer_ns();
+        a.trace[blockIdx.x * 4 + 2] = 0;
+        a.trace[blockIdx.x * 4 + 3] = 0;
+    }
 
     if (tid == 0) {
         for (int i = 0; i < C::kStages; ++i) {
@@ -381,6 +402,7 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
             }
         }
 
+        if (a.trace && tid == 0) a.trace[blockIdx.x * 4 + 2] = global_timer_ns();
         // ---- publish this warp's partial ----
         const long long ub = cum[b] + static_cast<long long>(hg) * ns, ue = ub + ns;
         const int slot = (u_begin >= ub && u_begin < ue) ? 0 : 1;  // first segment of the CTA -> 0
@@ -419,46 +441,60 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
         named_bar_sync(1, kConsumerThreads);
         if (combine_flag) {
             // ---- last arriver: reduce every partial of (b, hg) and write the output ----
+            // Partials are merged in a fixed order (CTA index, then token slice), so the result does
+            // not depend on which CTA arrives last.  Loads are issued kCombineBatch sub-partials at a
+            // time, all independent, so the reduction costs a few L2 round trips, not one per partial.
             __threadfence();
             const int wpk = kConsumerWarps / a.hkt;  // warps (token slices) per kv head
+            const int nparts = lc - fc + 1;
+            for (int i = tid; i < nparts; i += kConsumerThreads) {
+                const long long cs = cta_start(units, fc + i, ncta);
+                const int sl = (cs >= ub && cs < ue) ? 0 : 1;
+                part_base[i] = ((fc + i) * 2 + sl) * kConsumerWarps;
+            }
+            named_bar_sync(1, kConsumerThreads);
+            const int nsub = nparts * wpk;
             const int total = a.hkt * G * (D / 4);
             for (int idx = tid; idx < total; idx += kConsumerThreads) {
                 const int d4 = idx % (D / 4);
                 const int rr = (idx / (D / 4)) % G;
                 const int h2 = idx / (D / 4) / G;
-                float m_star = -INFINITY;
-                for (int c = fc; c <= lc; ++c) {
-                    const long long cs = cta_start(units, c, ncta);
-                    const int sl = (cs >= ub && cs < ue) ? 0 : 1;
-                    for (int w = 0; w < wpk; ++w) {
-                        const int64_t part = (static_cast<int64_t>(c) * 2 + sl) * kConsumerWarps + w * a.hkt + h2;
-                        m_star = fmaxf(m_star, __ldcg(a.ws_ml + part * (kPartRows * 2) + rr * 2));
-                    }
-                }
+                float m_run = -INFINITY, l_run = 0.f;
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                float lsum = 0.f;
-                if (m_star != -INFINITY) {
-                    for (int c = fc; c <= lc; ++c) {
-                        const long long cs = cta_start(units, c, ncta);
-                        const int sl = (cs >= ub && cs < ue) ? 0 : 1;
-                        for (int w = 0; w < wpk; ++w) {
-                            const int64_t part =
-                                (static_cast<int64_t>(c) * 2 + sl) * kConsumerWarps + w * a.hkt + h2;
-                            const float2 ml = __ldcg(reinterpret_cast<const float2 *>(
-                                a.ws_ml + part * (kPartRows * 2) + rr * 2));
-                            if (ml.x == -INFINITY) continue;
-                            const float wgt = fast_exp2(ml.x - m_star);
-                            const float4 ov = __ldcg(reinterpret_cast<const float4 *>(
-                                a.ws_o + part * (kPartRows * D) + rr * D + d4 * 4));
-                            acc.x += wgt * ov.x;
-                            acc.y += wgt * ov.y;
-                            acc.z += wgt * ov.z;
-                            acc.w += wgt * ov.w;
-                            lsum += wgt * ml.y;
+                for (int s0 = 0; s0 < nsub; s0 += kCombineBatch) {
+                    float2 ml[kCombineBatch];
+                    float4 ov[kCombineBatch];
+#pragma unroll
+                    for (int j = 0; j < kCombineBatch; ++j) {
+                        const int sidx = s0 + j;
+                        ml[j] = make_float2(-INFINITY, 0.f);
+                        ov[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (sidx < nsub) {
+                            const int64_t part = part_base[sidx / wpk] + (sidx % wpk) * a.hkt + h2;
+                            ml[j] = __ldcg(reinterpret_cast<const float2 *>(a.ws_ml + part * (kPartRows * 2) + rr * 2));
+                            ov[j] = __ldcg(reinterpret_cast<const float4 *>(a.ws_o + part * (kPartRows * D) + rr * D + d4 * 4));
                         }
                     }
+                    float m_new = m_run;
+#pragma unroll
+                    for (int j = 0; j < kCombineBatch; ++j) m_new = fmaxf(m_new, ml[j].x);
+                    if (m_new == -INFINITY) continue;  // nothing but empty partials so far
+                    const float c0 = fast_exp2(m_run - m_new);  // m_run = -inf -> 0
+                    acc.x *= c0; acc.y *= c0; acc.z *= c0; acc.w *= c0;
+                    l_run *= c0;
+#pragma unroll
+                    for (int j = 0; j < kCombineBatch; ++j) {
+                        const float wgt = fast_exp2(ml[j].x - m_new);  // empty partial: exp2(-inf) = 0
+                        acc.x += wgt * ov[j].x;
+                        acc.y += wgt * ov[j].y;
+                        acc.z += wgt * ov[j].z;
+                        acc.w += wgt * ov[j].w;
+                        l_run += wgt * ml[j].y;
+                    }
+                    m_run = m_new;
                 }
-                const float inv = (lsum == 0.f || lsum != lsum) ? 1.f : 1.f / lsum;
+                const bool empty = (l_run == 0.f || l_run != l_run);
+                const float inv = empty ? 1.f : 1.f / l_run;
                 const int head = (hg * a.hkt + h2) * G + rr;
                 T *op = static_cast<T *>(p.o) + b * p.o_bs + static_cast<int64_t>(head) * p.o_hs + d4 * 4;
                 uint2 packed;
@@ -467,14 +503,14 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
                 *reinterpret_cast<uint2 *>(op) = packed;
                 if (d4 == 0 && p.lse)
                     p.lse[static_cast<int64_t>(b) * p.h + head] =
-                        (lsum == 0.f || lsum != lsum) ? INFINITY
-                                                      : m_star * 0.6931471805599453f + __logf(lsum);
+                        empty ? INFINITY : m_run * 0.6931471805599453f + __logf(l_run);
             }
             if (tid == 0) a.counters[b * a.hg + hg] = 0;  // self-cleaning for the next launch
         }
         named_bar_sync(1, kConsumerThreads);  // combine_flag / slot 1 may be reused by the next segment
         u += n;
     }
+    if (a.trace && tid == 0) a.trace[blockIdx.x * 4 + 3] = global_timer_ns();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -522,6 +558,8 @@ bool make_kv_map(CUtensorMap *out, const void *ptr, int64_t rs, int64_t hs, int6
     cache.push_back(MapEntry{key, *out});
     return true;
 }
+
+void *g_decode_trace = nullptr;
 
 template <typename T, int D>
 bool launch_decode(const CUtensorMap &mk, const CUtensorMap &mv, const DecodeArgs &a,
@@ -580,7 +618,7 @@ int try_launch_decode_paged(const MhaParams &p, bool is_bf16, int64_t max_units_
     // more CTAs than the upper bound of units.
     const int64_t units_ub = static_cast<int64_t>(p.b) * hg * ((p.seqlen_k + tok - 1) / tok);
     (void)max_units_hint;
-    a.num_ctas = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(di.sm_count, units_ub)));
+    a.num_ctas = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min(di.sm_count, kMaxCtas), units_ub)));
 
     const size_t counters_bytes = kMaxCounters * sizeof(int);
     const size_t ml_bytes = static_cast<size_t>(di.sm_count) * 2 * kConsumerWarps * kPartRows * 2 * sizeof(float);
@@ -590,6 +628,7 @@ int try_launch_decode_paged(const MhaParams &p, bool is_bf16, int64_t max_units_
     a.counters = reinterpret_cast<int *>(ws);
     a.ws_ml = reinterpret_cast<float *>(ws + counters_bytes);
     a.ws_o = reinterpret_cast<float *>(ws + counters_bytes + ml_bytes);
+    a.trace = static_cast<unsigned long long *>(g_decode_trace);
 
     CUtensorMap mk, mv;
     if (!make_kv_map(&mk, p.k, p.k_rs, p.k_hs, p.k_bs, p.page, p.h_k, p.d, tb, hkt, is_bf16)) return -1;
@@ -602,5 +641,7 @@ int try_launch_decode_paged(const MhaParams &p, bool is_bf16, int64_t max_units_
                          : launch_decode<__half, 64>(mk, mv, a, stream);
     return ok ? 1 : -1;
 }
+
+void set_decode_trace(void *device_buf) { g_decode_trace = device_buf; }
 
 }  // namespace atoma

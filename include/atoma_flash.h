@@ -140,6 +140,11 @@ void swap_blocks_batched(void *dst_base, const void *src_base, const int64_t *sr
 void atoma_gemm_bf16_tn(const void *x, const void *w, void *y, int64_t T, int64_t N, int64_t K,
                         int64_t ldx, int64_t ldw, int64_t ldy, atoma_stream_t stream);
 
+/* Diagnostics: when device_buf is non-null every CTA of the paged decode kernel writes four
+ * uint64 {sm id, start, end of its last KV segment, end} (globaltimer ns) at device_buf[4*cta..];
+ * the buffer must hold 4 * #SM entries.  Pass NULL to switch it off (the default). */
+void atoma_debug_decode_trace(void *device_buf);
+
 /* 0 = last call on this thread succeeded; otherwise a negative atoma code or a cudaError_t. */
 int atoma_last_status(void);
 /* Human-readable text for the last non-zero status on this thread ("" if none). */
