@@ -69,7 +69,7 @@ struct DecodeArgs {
 
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
     return t;
 }
 __device__ __forceinline__ unsigned sm_id() {

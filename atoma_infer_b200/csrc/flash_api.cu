@@ -19,6 +19,7 @@ bool launch_attention_tile(const MhaParams &p, bool is_bf16, cudaStream_t stream
 int try_launch_decode_paged(const MhaParams &p, bool is_bf16, int64_t max_units_hint,
                             cudaStream_t stream);
 void set_decode_trace(void *device_buf);
+void set_gemm_trace(void *device_buf);
 bool launch_gemm_bf16_tn(const void *x, const void *w, void *y, int64_t T, int64_t N, int64_t K,
                          int64_t ldx, int64_t ldw, int64_t ldy, cudaStream_t stream);
 
@@ -275,6 +276,7 @@ extern "C" void atoma_gemm_bf16_tn(const void *x, const void *w, void *y, int64_
 }
 
 extern "C" void atoma_debug_decode_trace(void *device_buf) { set_decode_trace(device_buf); }
+extern "C" void atoma_debug_gemm_trace(void *device_buf) { set_gemm_trace(device_buf); }
 extern "C" int atoma_last_status(void) { return t_status; }
 extern "C" const char *atoma_last_error(void) { return t_error; }
 extern "C" const char *atoma_last_mha_path(void) { return t_path; }

@@ -144,6 +144,8 @@ void atoma_gemm_bf16_tn(const void *x, const void *w, void *y, int64_t T, int64_
  * uint64 {sm id, start, end of its last KV segment, end} (globaltimer ns) at device_buf[4*cta..];
  * the buffer must hold 4 * #SM entries.  Pass NULL to switch it off (the default). */
 void atoma_debug_decode_trace(void *device_buf);
+/* Same for the projection GEMM: {start, first operand tile landed, last accumulator complete, end}. */
+void atoma_debug_gemm_trace(void *device_buf);
 
 /* 0 = last call on this thread succeeded; otherwise a negative atoma code or a cudaError_t. */
 int atoma_last_status(void);
