@@ -173,6 +173,8 @@ reshape_and_cache_flash_vec_kernel(const char *__restrict__ key, const char *__r
                                    int chunks_per_token, int64_t key_stride_b,
                                    int64_t value_stride_b, int64_t block_stride_b,
                                    int64_t row_bytes, int64_t block_size) {
+    pdl_launch_dependents();
+    pdl_wait();  // key / value come from the kernel before this one in the stream
     const int64_t total = num_tokens * chunks_per_token;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kRcThreads;
     for (int64_t base = static_cast<int64_t>(blockIdx.x) * kRcThreads + threadIdx.x; base < total;
@@ -311,11 +313,12 @@ extern "C" void reshape_and_cache_flash(void *key, void *value, void *key_cache,
         const DeviceInfo &di = current_device_info();
         const int64_t want = (total + kRcThreads * kRcUnroll - 1) / (kRcThreads * kRcUnroll);
         const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, di.sm_count * 8)));
-        reshape_and_cache_flash_vec_kernel<<<grid, kRcThreads, 0, stream>>>(
-            static_cast<const char *>(key), static_cast<const char *>(value),
-            static_cast<char *>(key_cache), static_cast<char *>(value_cache), slot_mapping,
-            num_tokens, chunks, key_stride * 2, value_stride * 2, block_stride * 2, row_bytes,
-            block_size);
+        cudaError_t e = launch_ex(reshape_and_cache_flash_vec_kernel, dim3(grid), dim3(kRcThreads), 0, stream,
+                                  static_cast<const char *>(key), static_cast<const char *>(value),
+                                  static_cast<char *>(key_cache), static_cast<char *>(value_cache),
+                                  static_cast<const int64_t *>(slot_mapping), num_tokens, chunks, key_stride * 2,
+                                  value_stride * 2, block_stride * 2, row_bytes, block_size);
+        if (e != cudaSuccess) set_status(static_cast<int>(e), "reshape_and_cache_flash: %s", cudaGetErrorString(e));
     } else {
         const int threads = static_cast<int>(std::min<int64_t>(n, 512));
         reshape_and_cache_flash_scalar_kernel<<<static_cast<unsigned>(num_tokens), threads, 0, stream>>>(

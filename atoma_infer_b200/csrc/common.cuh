@@ -45,6 +45,35 @@ const DeviceInfo &current_device_info();
 enum : int { kWorkspaceDecode = 0, kWorkspaceSwapMap = 1, kWorkspaceGemm = 2, kWorkspaceTags = 3 };
 void *get_workspace(cudaStream_t stream, size_t bytes, int tag);
 
+// Launch mode (process-wide, atoma_set_launch_mode): programmatic dependent launch between this
+// library's kernels, and "weights are immutable" (the GEMM may prefetch W before its grid
+// dependency resolves).
+enum : int { kLaunchPdl = 1, kLaunchConstWeights = 2 };
+int launch_flags();
+
+#if defined(__CUDACC__)
+// Kernel launch with the programmatic-stream-serialization attribute when PDL is enabled: the
+// kernel may start while its predecessor in the stream drains; it must execute pdl_wait() before
+// touching anything the predecessor produces (every kernel launched through here does).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                      Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (launch_flags() & kLaunchPdl) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                   const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -59,6 +88,12 @@ EncodeTiledFn get_encode_tiled();
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- programmatic dependent launch (no-ops when the kernel was launched without the attribute) ----
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 // ---- mbarrier ----

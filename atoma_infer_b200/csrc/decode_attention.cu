@@ -36,7 +36,9 @@ namespace {
 
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kDecodeThreads = kConsumerThreads + 32;  // + producer warp
+constexpr int kDecodeThreads = kConsumerThreads + 128;  // + the producer warpgroup (one warp issues TMA)
+constexpr int kProducerRegs = 56;    // setmaxnreg: the producer warpgroup hands its registers ...
+constexpr int kConsumerRegs = 216;   // ... to the two consumer warpgroups (168 + 112 * 128 / 256)
 constexpr int kStageRows = 128;                        // (token, head) rows per stage
 constexpr int kMaxBatch = 2047;
 constexpr int kMaxCounters = 16384;                    // B * head groups
@@ -94,6 +96,97 @@ __device__ __forceinline__ int cta_of_unit(long long units, long long u, int num
     return static_cast<int>(((u + 1) * num_ctas + units - 1) / units - 1);
 }
 
+// Reduction of every partial of one (sequence, kv head) by ONE warp (the last to arrive for that
+// head).  Partials are merged in CTA-index order whoever arrives last, four outputs per lane and
+// four partials in flight at a time (16-byte loads), so the result is bit-reproducible and the cost
+// is a few L2 round trips.
+template <typename T, int D>
+__device__ __forceinline__ void combine_head(const DecodeArgs &a, long long units, int ncta, int fc, int lc,
+                                             long long ub, long long ue, int b, int kvh, int hh, int G,
+                                             int lane) {
+    const MhaParams &p = a.p;
+    constexpr int C4 = D / 4;
+    const int nparts = lc - fc + 1;
+    const int total = G * C4;
+    for (int g0 = 0; g0 < total; g0 += 128) {
+        bool ok[4];
+        int rr[4], d4[4];
+        float m_run[4], l_run[4];
+        float4 acc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = g0 + lane + 32 * k;
+            ok[k] = idx < total;
+            rr[k] = ok[k] ? idx / C4 : 0;
+            d4[k] = idx % C4;
+            m_run[k] = -INFINITY;
+            l_run[k] = 0.f;
+            acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int pc = 0; pc < nparts; pc += 32) {
+            int mybase = 0;  // lane j: workspace index of contributor pc + j
+            if (pc + lane < nparts) {
+                const int c = fc + pc + lane;
+                const long long cs = cta_start(units, c, ncta);
+                mybase = (c * 2 + ((cs >= ub && cs < ue) ? 0 : 1)) * kConsumerWarps + hh;
+            }
+            const int nchunk = min(32, nparts - pc);
+            for (int s0 = 0; s0 < nchunk; s0 += 4) {
+                float2 ml[4][4];
+                float4 ov[4][4];
+#pragma unroll
+                for (int ss = 0; ss < 4; ++ss) {
+                    // Loads are unconditional (clamped to a valid partial) so that all 32 of them are
+                    // in flight together; out-of-range ones get weight exp2(-inf) = 0 below.
+                    const int64_t base = __shfl_sync(0xffffffffu, mybase, min(s0 + ss, nchunk - 1));
+                    const bool pv = s0 + ss < nchunk;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        ml[ss][k] = __ldcg(reinterpret_cast<const float2 *>(a.ws_ml + base * (kPartRows * 2) + rr[k] * 2));
+                        ov[ss][k] = __ldcg(reinterpret_cast<const float4 *>(a.ws_o + base * (kPartRows * D) + rr[k] * D + d4[k] * 4));
+                        if (!(pv && ok[k])) ml[ss][k].x = -INFINITY;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float m_new = m_run[k];
+#pragma unroll
+                    for (int ss = 0; ss < 4; ++ss) m_new = fmaxf(m_new, ml[ss][k].x);
+                    if (m_new == -INFINITY) continue;  // nothing but empty partials so far
+                    const float c0 = fast_exp2(m_run[k] - m_new);  // m_run = -inf -> 0
+                    acc[k].x *= c0; acc[k].y *= c0; acc[k].z *= c0; acc[k].w *= c0;
+                    l_run[k] *= c0;
+#pragma unroll
+                    for (int ss = 0; ss < 4; ++ss) {
+                        const float wgt = fast_exp2(ml[ss][k].x - m_new);  // empty partial: exp2(-inf) = 0
+                        acc[k].x += wgt * ov[ss][k].x;
+                        acc[k].y += wgt * ov[ss][k].y;
+                        acc[k].z += wgt * ov[ss][k].z;
+                        acc[k].w += wgt * ov[ss][k].w;
+                        l_run[k] += wgt * ml[ss][k].y;
+                    }
+                    m_run[k] = m_new;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!ok[k]) continue;
+            const bool empty = (l_run[k] == 0.f || l_run[k] != l_run[k]);
+            const float inv = empty ? 1.f : 1.f / l_run[k];
+            const int head = kvh * G + rr[k];
+            T *op = static_cast<T *>(p.o) + b * p.o_bs + static_cast<int64_t>(head) * p.o_hs + d4[k] * 4;
+            uint2 packed;
+            packed.x = pack2<T>(acc[k].x * inv, acc[k].y * inv);
+            packed.y = pack2<T>(acc[k].z * inv, acc[k].w * inv);
+            *reinterpret_cast<uint2 *>(op) = packed;
+            if (d4[k] == 0 && p.lse)
+                p.lse[static_cast<int64_t>(b) * p.h + head] =
+                    empty ? INFINITY : m_run[k] * 0.6931471805599453f + __logf(l_run[k]);
+        }
+    }
+}
+
 template <typename T, int D>
 __global__ void __launch_bounds__(kDecodeThreads, 1)
 decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
@@ -110,12 +203,7 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int B = p.b;
-    if (a.trace && tid == 0) {
-        a.trace[blockIdx.x * 4 + 0] = sm_id();
-        a.trace[blockIdx.x * 4 + 1] = global_timer_ns();
-        a.trace[blockIdx.x * 4 + 2] = 0;
-        a.trace[blockIdx.x * 4 + 3] = 0;
-    }
+    const unsigned long long t_start = a.trace ? global_timer_ns() : 0ull;
 
     if (tid == 0) {
         for (int i = 0; i < C::kStages; ++i) {
@@ -128,6 +216,17 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
     if (warp == kConsumerWarps && lane == 0) {
         tma_prefetch_desc(&map_k);
         tma_prefetch_desc(&map_v);
+    }
+    // Programmatic dependent launch: everything above overlaps the previous kernel's tail; nothing
+    // below (sequence lengths, block table, q, caches, workspace, outputs) is touched before the
+    // previous kernel in the stream has completed.
+    pdl_launch_dependents();
+    pdl_wait();
+    if (a.trace && tid == 0) {
+        a.trace[blockIdx.x * 8 + 0] = sm_id();
+        a.trace[blockIdx.x * 8 + 1] = t_start;
+        a.trace[blockIdx.x * 8 + 2] = 0;
+        a.trace[blockIdx.x * 8 + 3] = 0;
     }
     // units per sequence -> exclusive prefix sum in cum[]
     for (int i = tid; i < B; i += kDecodeThreads) {
@@ -180,8 +279,10 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
     int stage = 0;
     uint32_t phase = 0;
 
-    if (warp == kConsumerWarps) {
-        // =========================== producer warp ===========================
+    if (warp >= kConsumerWarps) {
+        // =========================== producer warpgroup ===========================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
+        if (warp != kConsumerWarps) return;  // warps 9..11 only lend their registers
         long long u = u_begin;
         int b = 0;
         while (u < u_end) {
@@ -252,6 +353,7 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
     }
 
     // ============================== consumer warps ==============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
     const int g = lane >> 2, t4 = lane & 3;
     const int hh = warp % a.hkt;          // kv head within the group
     const int ts = warp / a.hkt;          // 16-token slice within the stage
@@ -402,7 +504,7 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
             }
         }
 
-        if (a.trace && tid == 0) a.trace[blockIdx.x * 4 + 2] = global_timer_ns();
+        if (a.trace && tid == 0) a.trace[blockIdx.x * 8 + 2] = global_timer_ns();
         // ---- publish this warp's partial ----
         const long long ub = cum[b] + static_cast<long long>(hg) * ns, ue = ub + ns;
         const int slot = (u_begin >= ub && u_begin < ue) ? 0 : 1;  // first segment of the CTA -> 0
@@ -431,9 +533,31 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
                     __stcg(reinterpret_cast<float2 *>(pml + (g + 8) * 2), make_float2(m_run[1], l_run[1]));
             }
         }
+        const int fc = cta_of_unit(units, ub, ncta), lc = cta_of_unit(units, ue - 1, ncta);
+        if (a.hkt == kConsumerWarps) {
+            // One warp per kv head (Hkv a multiple of 8): every head is published and reduced on its
+            // own — no CTA-wide barrier, and the 8 reductions of a sequence land on whichever warps
+            // arrive last, usually on different SMs.
+            __threadfence();
+            __syncwarp();
+            if (a.trace && tid == 0) a.trace[blockIdx.x * 8 + 4] = global_timer_ns();
+            int *ctr = &a.counters[b * p.h_k + kvh];
+            int old = 0;
+            if (lane == 0) old = atomicAdd(ctr, 1);
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (a.trace && tid == 0) a.trace[blockIdx.x * 8 + 5] = global_timer_ns();
+            if (old == lc - fc) {
+                __threadfence();
+                if (a.trace && lane == 0) a.trace[blockIdx.x * 8 + 6] = global_timer_ns();
+                combine_head<T, D>(a, units, ncta, fc, lc, ub, ue, b, kvh, hh, G, lane);
+                if (lane == 0) *ctr = 0;  // self-cleaning for the next launch
+                if (a.trace && lane == 0) a.trace[blockIdx.x * 8 + 7] = global_timer_ns();
+            }
+            u += n;
+            continue;
+        }
         __threadfence();
         named_bar_sync(1, kConsumerThreads);
-        const int fc = cta_of_unit(units, ub, ncta), lc = cta_of_unit(units, ue - 1, ncta);
         if (tid == 0) {
             const int old = atomicAdd(&a.counters[b * a.hg + hg], 1);
             combine_flag = (old == lc - fc) ? 1 : 0;
@@ -466,14 +590,12 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
                     float4 ov[kCombineBatch];
 #pragma unroll
                     for (int j = 0; j < kCombineBatch; ++j) {
-                        const int sidx = s0 + j;
-                        ml[j] = make_float2(-INFINITY, 0.f);
-                        ov[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (sidx < nsub) {
-                            const int64_t part = part_base[sidx / wpk] + (sidx % wpk) * a.hkt + h2;
-                            ml[j] = __ldcg(reinterpret_cast<const float2 *>(a.ws_ml + part * (kPartRows * 2) + rr * 2));
-                            ov[j] = __ldcg(reinterpret_cast<const float4 *>(a.ws_o + part * (kPartRows * D) + rr * D + d4 * 4));
-                        }
+                        // unconditional loads (clamped), masked afterwards: all in flight together
+                        const int sidx = min(s0 + j, nsub - 1);
+                        const int64_t part = part_base[sidx / wpk] + (sidx % wpk) * a.hkt + h2;
+                        ml[j] = __ldcg(reinterpret_cast<const float2 *>(a.ws_ml + part * (kPartRows * 2) + rr * 2));
+                        ov[j] = __ldcg(reinterpret_cast<const float4 *>(a.ws_o + part * (kPartRows * D) + rr * D + d4 * 4));
+                        if (s0 + j >= nsub) ml[j].x = -INFINITY;
                     }
                     float m_new = m_run;
 #pragma unroll
@@ -510,7 +632,7 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
         named_bar_sync(1, kConsumerThreads);  // combine_flag / slot 1 may be reused by the next segment
         u += n;
     }
-    if (a.trace && tid == 0) a.trace[blockIdx.x * 4 + 3] = global_timer_ns();
+    if (a.trace && tid == 0) a.trace[blockIdx.x * 8 + 3] = global_timer_ns();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -572,8 +694,12 @@ bool launch_decode(const CUtensorMap &mk, const CUtensorMap &mv, const DecodeArg
                              static_cast<int>(smem));
         attr_dev = di.ordinal;
     }
-    decode_paged_kernel<T, D><<<a.num_ctas, kDecodeThreads, smem, stream>>>(mk, mv, a);
+    cudaError_t e = launch_ex(decode_paged_kernel<T, D>, dim3(a.num_ctas), dim3(kDecodeThreads), smem, stream, mk, mv, a);
     note_launch();
+    if (e != cudaSuccess) {
+        set_status(static_cast<int>(e), "decode_paged_kernel: %s", cudaGetErrorString(e));
+        return false;
+    }
     return check_launch("decode_paged_kernel");
 }
 
@@ -599,7 +725,7 @@ int try_launch_decode_paged(const MhaParams &p, bool is_bf16, int64_t max_units_
     int hkt = 8;
     while (hkt > 1 && p.h_k % hkt != 0) hkt >>= 1;
     const int hg = p.h_k / hkt;
-    if (static_cast<int64_t>(p.b) * hg > kMaxCounters) return 0;
+    if (static_cast<int64_t>(p.b) * p.h_k > kMaxCounters) return 0;
     const int tok = kStageRows / hkt;
     int tb = tok;
     while (tb > 16 && p.page % tb != 0) tb >>= 1;

@@ -8,6 +8,7 @@
 #include "mha_params.h"
 
 #include <cstdarg>
+#include <atomic>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -29,6 +30,11 @@ thread_local char t_error[512] = "";
 thread_local const char *t_path = "";
 thread_local int64_t t_launches = 0;
 }  // namespace
+
+namespace {
+std::atomic<int> g_launch_flags{0};
+}
+int launch_flags() { return g_launch_flags.load(std::memory_order_relaxed); }
 
 void set_status(int code, const char *fmt, ...) {
     t_status = code;
@@ -277,6 +283,8 @@ extern "C" void atoma_gemm_bf16_tn(const void *x, const void *w, void *y, int64_
 
 extern "C" void atoma_debug_decode_trace(void *device_buf) { set_decode_trace(device_buf); }
 extern "C" void atoma_debug_gemm_trace(void *device_buf) { set_gemm_trace(device_buf); }
+extern "C" void atoma_set_launch_mode(int flags) { g_launch_flags.store(flags, std::memory_order_relaxed); }
+extern "C" int atoma_get_launch_mode(void) { return launch_flags(); }
 extern "C" int atoma_last_status(void) { return t_status; }
 extern "C" const char *atoma_last_error(void) { return t_error; }
 extern "C" const char *atoma_last_mha_path(void) { return t_path; }

@@ -47,6 +47,7 @@ struct GemmArgs {
     int is_bf16;
     int *counters;    // [tiles], zero between launches
     float *ws;        // [cta][2][t_pad][128] fp32 partials
+    int prefetch_w;   // W is immutable: stream it before the grid dependency resolves
     unsigned long long *trace;  // diagnostics (atoma_debug_gemm_trace): [cta][4] or null
 };
 
@@ -74,7 +75,7 @@ gemm_tn_stream_kernel(const __grid_constant__ CUtensorMap map_w,
     __shared__ int part_slot[kGemmMaxCtas];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (a.trace && tid == 0) a.trace[blockIdx.x * 4 + 0] = g_timer_ns();
+    const unsigned long long t_start = a.trace ? g_timer_ns() : 0ull;
     const int x_bytes = a.t_pad * 128;
     const int stage_bytes = kWBytes + x_bytes;
 
@@ -108,9 +109,32 @@ gemm_tn_stream_kernel(const __grid_constant__ CUtensorMap map_w,
     if (warp == 0) {
         // ============================ TMA producer ============================
         if (lane == 0) {
+            pdl_launch_dependents();
             int stage = 0;
             uint32_t phase = 0;
-            for (long long u = u_begin; u < u_end; ++u) {
+            long long u = u_begin;
+            // Programmatic dependent launch: W does not depend on the previous kernel, so the ring is
+            // filled with weight tiles while the predecessor drains; x (its output) follows the wait.
+            int pre = 0;
+            if (a.prefetch_w) {
+                pre = static_cast<int>(min(static_cast<long long>(a.stages), u_end - u_begin));
+                for (int i = 0; i < pre; ++i) {
+                    const long long uu = u_begin + i;
+                    const int tile = static_cast<int>(uu / KB), kb = static_cast<int>(uu % KB);
+                    mbar_arrive_expect_tx(&full[i], stage_bytes);
+                    tma_load_2d(tiles + i * stage_bytes, &map_w, &full[i], kb * kBlockK, tile * kTileN, kL2EvictFirst);
+                }
+            }
+            pdl_wait();
+            if (a.trace) a.trace[blockIdx.x * 4 + 0] = t_start;
+            for (int i = 0; i < pre; ++i) {
+                const int kb = static_cast<int>((u_begin + i) % KB);
+                tma_load_2d(tiles + i * stage_bytes + kWBytes, &map_x, &full[i], kb * kBlockK, 0, kL2EvictLast);
+            }
+            u += pre;
+            stage = pre % a.stages;
+            phase = (pre == a.stages) ? 1u : 0u;
+            for (; u < u_end; ++u) {
                 const int tile = static_cast<int>(u / KB), kb = static_cast<int>(u % KB);
                 mbar_wait(&empty[stage], phase ^ 1);
                 unsigned char *ws = tiles + stage * stage_bytes;
@@ -126,6 +150,7 @@ gemm_tn_stream_kernel(const __grid_constant__ CUtensorMap map_w,
         }
     } else if (warp == 1) {
         // ============================ MMA issuer ============================
+        pdl_wait();
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_f16(kTileN, a.t_pad, a.is_bf16 != 0);
             int stage = 0;
@@ -163,6 +188,7 @@ gemm_tn_stream_kernel(const __grid_constant__ CUtensorMap map_w,
         }
     } else {
         // ============================ epilogue warps (2..5) ============================
+        pdl_wait();
         const int quad = warp & 3;             // TMEM lane quadrant this warp may read
         const int row = quad * 32 + lane;      // weight row within the tile
         const int etid = tid - 64;             // 0..127
@@ -374,6 +400,7 @@ bool launch_stream_gemm(const void *x, const void *w, void *y, int T, int64_t N,
     a.counters = reinterpret_cast<int *>(ws);
     a.ws = reinterpret_cast<float *>(ws + counters_bytes);
     a.trace = static_cast<unsigned long long *>(g_gemm_trace);
+    a.prefetch_w = ((launch_flags() & (kLaunchPdl | kLaunchConstWeights)) == (kLaunchPdl | kLaunchConstWeights)) ? 1 : 0;
 
     CUtensorMap mw, mx;
     if (!make_operand_map(&mw, w, N, K, ldw, kTileN, is_bf16)) return false;
@@ -390,8 +417,12 @@ bool launch_stream_gemm(const void *x, const void *w, void *y, int T, int64_t N,
         }
         attr_dev = di.ordinal;
     }
-    gemm_tn_stream_kernel<<<grid, kGemmThreads, smem, stream>>>(mw, mx, a);
+    cudaError_t e = launch_ex(gemm_tn_stream_kernel, dim3(grid), dim3(kGemmThreads), smem, stream, mw, mx, a);
     note_launch();
+    if (e != cudaSuccess) {
+        set_status(static_cast<int>(e), "gemm_tn_stream_kernel: %s", cudaGetErrorString(e));
+        return false;
+    }
     return check_launch("gemm_tn_stream_kernel");
 }
 

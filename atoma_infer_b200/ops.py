@@ -265,6 +265,14 @@ def gemm_bf16_tn(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] =
     return out
 
 
+LAUNCH_PDL, LAUNCH_CONST_WEIGHTS = 1, 2
+
+
+def set_launch_mode(pdl: bool = False, const_weights: bool = False) -> None:
+    """include/atoma_flash.h: atoma_set_launch_mode (process-wide)."""
+    _lib.lib().atoma_set_launch_mode((LAUNCH_PDL if pdl else 0) | (LAUNCH_CONST_WEIGHTS if const_weights else 0))
+
+
 def last_mha_path() -> str:
     return _lib.lib().atoma_last_mha_path().decode()
 

@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--gemm", default="auto", choices=["auto", "atoma", "cublas"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch between our kernels")
     return ap.parse_args()
 
 
@@ -295,7 +296,7 @@ def main():
     gemm = args.gemm
     if gemm == "auto":
         gemm = "cublas"
-        if args.impl == "ours" and os.environ.get("ATOMA_BENCH_GEMM", "") == "atoma":
+        if args.impl == "ours" and os.environ.get("ATOMA_BENCH_GEMM", "cublas") == "atoma":
             # use the hand-written GEMM once it is built (the placeholder reports "unsupported")
             try:
                 a = torch.zeros((BATCH, 64), device=dev, dtype=torch.bfloat16)
@@ -305,6 +306,9 @@ def main():
             except Exception:
                 gemm = "cublas"
 
+    if args.impl == "ours":
+        # weights are immutable during a decode step: the GEMM may stream them ahead of its dependency
+        ops.set_launch_mode(pdl=not args.no_pdl, const_weights=not args.no_pdl)
     st = State(torch, rank if args.impl == "ours" else 0, tp, args.layers, dev)
     step = make_step(st, args.impl, gemm, dist)
     stream = torch.cuda.current_stream()
@@ -392,15 +396,36 @@ def main():
             plan = ops.flash_attn_kv_cache_plan(qs, st.kv[l][0], st.kv[l][1], st.scale, block_table=st.devt["bt"],
                                                 seqlens_k=st.devt["lens"], window_size_right=0, num_sms=sms)
             return ref.execute(plan, qs, sync=False)
-    for l in range(st.layers):
-        attn_only(l)
+    def attn_pass():
+        for l in range(st.layers):
+            attn_only(l)
+
+    attn_pass()
+    torch.cuda.synchronize()
+    attn_run = attn_pass
+    if args.impl == "ours" and graph is not None:
+        # same launch mechanism as the timed step: replay a captured pass (no host launch overhead)
+        try:
+            side2 = torch.cuda.Stream()
+            side2.wait_stream(stream)
+            with torch.cuda.stream(side2):
+                attn_pass()
+            stream.wait_stream(side2)
+            torch.cuda.synchronize()
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2, stream=side2):
+                attn_pass()
+            attn_run = g2.replay
+        except Exception as e:  # pragma: no cover
+            print(f"[bench] attention-only graph capture failed ({e})", file=sys.stderr)
+            torch.cuda.synchronize()
+    attn_run()
     torch.cuda.synchronize()
     reps = 3
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record()
     for _ in range(reps):
-        for l in range(st.layers):
-            attn_only(l)
+        attn_run()
     k1.record()
     torch.cuda.synchronize()
     us_kernel = k0.elapsed_time(k1) * 1e3 / (reps * st.layers)
@@ -444,7 +469,8 @@ def main():
                 "batch": BATCH, "ctx": CTX, "layers": st.layers, "heads": H, "kv_heads": HK, "head_dim": D,
                 "block_size": PAGE, "parallelism": f"tp{tp}",
                 "l2": "inputs larger than L2: 541 MB of KV per layer, 17.3 GB per step, distinct per layer",
-                "launch": "cuda graph replay" if graph is not None else "eager, one host thread",
+                "launch": ("cuda graph replay" if graph is not None else "eager, one host thread") +
+                          (", programmatic dependent launch" if args.impl == "ours" and not args.no_pdl else ""),
                 "gemm": "atoma tcgen05 kernel" if gemm == "atoma" else "cuBLAS via torch.matmul (library GEMM, as in the reference)",
                 "wall_ms_per_step": t_wall * 1e3 / args.steps,
             },

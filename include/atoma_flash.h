@@ -140,9 +140,26 @@ void swap_blocks_batched(void *dst_base, const void *src_base, const int64_t *sr
 void atoma_gemm_bf16_tn(const void *x, const void *w, void *y, int64_t T, int64_t N, int64_t K,
                         int64_t ldx, int64_t ldw, int64_t ldy, atoma_stream_t stream);
 
-/* Diagnostics: when device_buf is non-null every CTA of the paged decode kernel writes four
- * uint64 {sm id, start, end of its last KV segment, end} (globaltimer ns) at device_buf[4*cta..];
- * the buffer must hold 4 * #SM entries.  Pass NULL to switch it off (the default). */
+/*
+ * Process-wide launch mode, a bit set (default 0):
+ *   ATOMA_LAUNCH_PDL (1)           launch this library's kernels with programmatic dependent launch:
+ *                                  a kernel's prologue (barrier / TMEM / descriptor set-up) overlaps
+ *                                  the tail of the kernel before it in the stream; every kernel
+ *                                  waits for its predecessor to complete before it touches memory
+ *                                  the predecessor may produce.
+ *   ATOMA_LAUNCH_CONST_WEIGHTS (2) the `w` operand of atoma_gemm_bf16_tn is never written by work
+ *                                  in flight on the stream (inference weights): with PDL the GEMM
+ *                                  starts streaming W into shared memory before the predecessor ends.
+ */
+#define ATOMA_LAUNCH_PDL 1
+#define ATOMA_LAUNCH_CONST_WEIGHTS 2
+void atoma_set_launch_mode(int flags);
+int atoma_get_launch_mode(void);
+
+/* Diagnostics: when device_buf is non-null every CTA of the paged decode kernel writes eight
+ * uint64 {sm id, start, end of its last KV segment, end, partial published, arrival counted,
+ * reduction started, reduction finished} (globaltimer ns; the last two only on CTAs that reduce)
+ * at device_buf[8*cta..]; the buffer must hold 8 * #SM entries.  NULL switches it off (default). */
 void atoma_debug_decode_trace(void *device_buf);
 /* Same for the projection GEMM: {start, first operand tile landed, last accumulator complete, end}. */
 void atoma_debug_gemm_trace(void *device_buf);

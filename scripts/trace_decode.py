@@ -22,7 +22,7 @@ def main():
     sl = torch.full((B,), 4096, dtype=torch.int32, device=dev)
     L = _lib.lib()
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    trace = torch.zeros((sms, 4), dtype=torch.int64, device=dev)
+    trace = torch.zeros((sms, 8), dtype=torch.int64, device=dev)
     for i in range(6):
         ops.flash_attn_kv_cache_full(q, caches[i % 3][0], caches[i % 3][1], None, D ** -0.5, bt, sl, True)
     torch.cuda.synchronize()
@@ -37,6 +37,11 @@ def main():
     for name, x in (("start", start), ("last segment done", seg), ("end", end)):
         print(f"{name:18s} min {x.min():7.2f} p10 {np.percentile(x, 10):7.2f} median {np.median(x):7.2f} "
               f"p90 {np.percentile(x, 90):7.2f} max {x.max():7.2f}")
+    for name, col in (("published", 4), ("arrival counted", 5), ("reduce start", 6), ("reduce end", 7)):
+        m = t[:, col] > 0
+        x = (t[m, col] - t0) / 1e3
+        d = (t[m, col] - t[m, 2]) / 1e3
+        print(f"{name:18s} n={m.sum():3d} median {np.median(x):7.2f} max {x.max():7.2f}   after 'segment done': median {np.median(d):6.2f} max {d.max():6.2f}")
     order = np.argsort(end)
     print("slowest CTAs (cta, smid, start, seg, end):")
     for i in order[-8:]:
