@@ -7,4 +7,4 @@ library is loaded (and required — there is no fallback) on first use.
 from . import _lib  # noqa: F401
 from .ops import AtomaError  # noqa: F401
 
-__all__ = ["ops", "flash_attention", "AtomaError"]
+__all__ = ["ops", "flash_attention", "tp", "AtomaError"]

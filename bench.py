@@ -58,8 +58,10 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=L, help="debug only; the reported config needs 32")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--graph-tp", action="store_true", help="also capture the tensor-parallel step (NCCL inside the graph)")
     ap.add_argument("--gemm", default="auto", choices=["auto", "atoma", "cublas"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verbose", action="store_true", help="progress markers on stderr")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch between our kernels")
     return ap.parse_args()
 
@@ -121,7 +123,9 @@ class State:
 
     def __init__(self, torch, rank: int, world: int, layers: int, dev):
         self.torch, self.rank, self.world, self.layers, self.dev = torch, rank, world, layers, dev
-        self.h, self.hk = H // world, HK // world
+        from atoma_infer_b200.tp import HeadShard
+        self.shard = HeadShard(rank, world, H, HK, D)   # llama_nccl.rs:164-171
+        self.h, self.hk = self.shard.heads, self.shard.kv_heads
         self.nb = BATCH * MB + 64
         g = torch.Generator(device=dev).manual_seed(1234 + rank)
         bf = torch.bfloat16
@@ -204,21 +208,30 @@ def make_step(st: State, impl: str, gemm: str, dist):
                                             d["slots"].data_ptr(), kc.stride(0), BATCH, st.hk, D, PAGE,
                                             k.stride(0), v.stride(0), 1, stream0)
 
+    def layer(l, x, out=None):
+        """One layer of the path on this rank: x [B, hidden] -> partial (pre-all-reduce) o_proj output."""
+        qkv = mm(x, st.wqkv[l])                                   # [B, (h + 2 hk) D]
+        q = qkv[:, :nq].unflatten(1, (st.h, D)).unsqueeze(1)      # [B, 1, h, D] (strided view)
+        k = qkv[:, nq:nq + nkv].unflatten(1, (st.hk, D))          # [B, hk, D]
+        v = qkv[:, nq + nkv:].unflatten(1, (st.hk, D))
+        kc, vc = st.kv[l][0], st.kv[l][1]
+        cache_write(k, v, kc, vc)
+        o = attn(q, kc, vc, l)                                    # [B, 1, h, D]
+        y = mm(o.reshape(BATCH, nq), st.wo[l])                    # [B, hidden]
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
+
     def step():
         x = d["x"]
         for l in range(st.layers):
-            qkv = mm(x, st.wqkv[l])                                   # [B, (h + 2 hk) D]
-            q = qkv[:, :nq].unflatten(1, (st.h, D)).unsqueeze(1)      # [B, 1, h, D] (strided view)
-            k = qkv[:, nq:nq + nkv].unflatten(1, (st.hk, D))          # [B, hk, D]
-            v = qkv[:, nq + nkv:].unflatten(1, (st.hk, D))
-            kc, vc = st.kv[l][0], st.kv[l][1]
-            cache_write(k, v, kc, vc)
-            o = attn(q, kc, vc, l)                                    # [B, 1, h, D]
-            x = mm(o.reshape(BATCH, nq), st.wo[l])                    # [B, hidden]
+            x = layer(l, x)
             if st.world > 1:
                 dist.all_reduce(x)                                    # multi_gpu.rs:141-179
         st.out.copy_(x)
 
+    step.layer = layer
     return step
 
 
@@ -272,6 +285,10 @@ def main():
     if args.impl == "reference" and rank != 0:
         return  # rank 0 alone runs the reference arm
 
+    def mark(msg):
+        if args.verbose:
+            print(f"[bench r{rank}] {time.strftime('%H:%M:%S')} {msg}", file=sys.stderr, flush=True)
+
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU or PyTorch fallback for the product path)")
@@ -309,7 +326,9 @@ def main():
     if args.impl == "ours":
         # weights are immutable during a decode step: the GEMM may stream them ahead of its dependency
         ops.set_launch_mode(pdl=not args.no_pdl, const_weights=not args.no_pdl)
+    mark("init done, building state")
     st = State(torch, rank if args.impl == "ours" else 0, tp, args.layers, dev)
+    mark("state built")
     step = make_step(st, args.impl, gemm, dist)
     stream = torch.cuda.current_stream()
 
@@ -322,8 +341,10 @@ def main():
     ops.reset_launch_count()
     step()
     torch.cuda.synchronize()
+    mark("first eager step done")
     launches_per_step = ops.launch_count() if args.impl == "ours" else 0
-    use_graph = args.impl == "ours" and not args.no_graph
+    # NCCL collectives are launched eagerly: the tensor-parallel step is not graph-captured
+    use_graph = args.impl == "ours" and not args.no_graph and (world == 1 or args.graph_tp)
     graph = None
     if use_graph:
         try:
@@ -344,10 +365,42 @@ def main():
             graph = None
             torch.cuda.synchronize()
     run = graph.replay if graph is not None else step
+    layer_graphs = None
+    if args.impl == "ours" and world > 1 and graph is None and not args.no_graph:
+        # Tensor parallel: torch's NCCL collectives are launched eagerly (capturing them hangs with this
+        # torch/NCCL pair), everything between two all-reduces is one CUDA graph per layer.
+        try:
+            bufs = [torch.empty_like(st.out), torch.empty_like(st.out)]
+            side = torch.cuda.Stream()
+            side.wait_stream(stream)
+            with torch.cuda.stream(side):
+                for l in range(st.layers):
+                    step.layer(l, bufs[l % 2], out=bufs[(l + 1) % 2])
+            stream.wait_stream(side)
+            torch.cuda.synchronize()
+            layer_graphs = []
+            for l in range(st.layers):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    step.layer(l, bufs[l % 2], out=bufs[(l + 1) % 2])
+                layer_graphs.append(g)
+            torch.cuda.synchronize()
 
+            def run():
+                bufs[0].copy_(st.devt["x"])
+                for l, g in enumerate(layer_graphs):
+                    g.replay()
+                    dist.all_reduce(bufs[(l + 1) % 2])
+                st.out.copy_(bufs[st.layers % 2])
+        except Exception as e:  # pragma: no cover
+            print(f"[bench] per-layer graph capture failed ({e}); launching eagerly", file=sys.stderr)
+            layer_graphs = None
+            run = step
+            torch.cuda.synchronize()
     for _ in range(max(args.warmup, 3)):
         run()
     barrier()
+    mark("warm-up done")
 
     # ---- timed region 1: device-resident inputs, K steps, CUDA events ----
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -361,6 +414,7 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall0
     ms_dev = e0.elapsed_time(e1)
+    mark("timed region 1 done")
 
     # ---- timed region 2 (e2e): host buffers -> H2D -> step -> D2H, every step ----
     for _ in range(2):
@@ -379,6 +433,7 @@ def main():
     t_e2e_wall = time.perf_counter() - t0
     ms_e2e = max(e2.elapsed_time(e3), t_e2e_wall * 1e3)  # host wall-clock includes the syncs
     clocks = sampler.stop() if sampler else None
+    mark("timed region 2 done")
 
     # ---- dominant kernel alone: paged decode attention, one launch per layer (distinct caches) ----
     nq = st.h * D
@@ -403,7 +458,7 @@ def main():
     attn_pass()
     torch.cuda.synchronize()
     attn_run = attn_pass
-    if args.impl == "ours" and graph is not None:
+    if args.impl == "ours" and not args.no_graph:
         # same launch mechanism as the timed step: replay a captured pass (no host launch overhead)
         try:
             side2 = torch.cuda.Stream()
@@ -469,7 +524,9 @@ def main():
                 "batch": BATCH, "ctx": CTX, "layers": st.layers, "heads": H, "kv_heads": HK, "head_dim": D,
                 "block_size": PAGE, "parallelism": f"tp{tp}",
                 "l2": "inputs larger than L2: 541 MB of KV per layer, 17.3 GB per step, distinct per layer",
-                "launch": ("cuda graph replay" if graph is not None else "eager, one host thread") +
+                "launch": ("cuda graph replay" if graph is not None else
+                           "one cuda graph per layer + eager NCCL all-reduce" if layer_graphs is not None else
+                           "eager, one host thread") +
                           (", programmatic dependent launch" if args.impl == "ours" and not args.no_pdl else ""),
                 "gemm": "atoma tcgen05 kernel" if gemm == "atoma" else "cuBLAS via torch.matmul (library GEMM, as in the reference)",
                 "wall_ms_per_step": t_wall * 1e3 / args.steps,
