@@ -19,14 +19,6 @@ namespace {
 constexpr int kBM = 64;
 constexpr int kThreads = 128;
 
-__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void *gsrc, int src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc),
-                 "r"(src_bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
 struct SeqInfo {
     int q_start, len_q, len_k;
     int64_t q_off, o_off, k_off, v_off;

@@ -19,6 +19,7 @@ namespace atoma {
 bool launch_attention_tile(const MhaParams &p, bool is_bf16, cudaStream_t stream);
 int try_launch_decode_paged(const MhaParams &p, bool is_bf16, int64_t max_units_hint,
                             cudaStream_t stream);
+int try_launch_prefill_tc(const MhaParams &p, bool is_bf16, cudaStream_t stream);
 void set_decode_trace(void *device_buf);
 void set_gemm_trace(void *device_buf);
 bool launch_gemm_bf16_tn(const void *x, const void *w, void *y, int64_t T, int64_t N, int64_t K,
@@ -206,6 +207,12 @@ void run_mha_impl(void *q_ptr, void *k_ptr, void *v_ptr, void *o_ptr, void *soft
         return;
     }
     if (r < 0) return;
+    const int r2 = try_launch_prefill_tc(p, is_bf16 != 0, stream);
+    if (r2 == 1) {
+        set_mha_path("prefill_tc");
+        return;
+    }
+    if (r2 < 0) return;
     if (launch_attention_tile(p, is_bf16 != 0, stream)) set_mha_path("tile");
 }
 
