@@ -9,6 +9,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 namespace atoma {
@@ -370,7 +371,39 @@ extern "C" void swap_blocks_batched(void *dst_base, const void *src_base,
         set_status(kErrInvalidArg, "swap_blocks_batched: kind %d (0 d2d, 1 h2d, 2 d2h)", kind);
         return;
     }
-    // Host <-> device: merge runs of consecutive (src, dst) blocks into single async copies.
+    // Host <-> device.  Pinned (or registered) host memory is mapped into the device address space:
+    // the same one-launch bulk mover then reads / writes it over the host link, scattered blocks
+    // included, instead of one memcpy per block (the reference: csrc/src/ops.rs:158-216).
+    {
+        const void *hptr = kind == 1 ? src_base : dst_base;
+        cudaPointerAttributes pa;
+        std::memset(&pa, 0, sizeof(pa));
+        const bool mapped = cudaPointerGetAttributes(&pa, hptr) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+                            pa.devicePointer != nullptr;
+        cudaGetLastError();  // an unregistered pointer is not an error here
+        if (mapped && block_bytes % 16 == 0 && aligned16(dst_base) && aligned16(src_base)) {
+            int64_t *dmap = static_cast<int64_t *>(
+                get_workspace(stream, 2 * num_pairs * sizeof(int64_t), kWorkspaceSwapMap));
+            if (!dmap) return;
+            cudaMemcpyAsync(dmap, src_blocks, num_pairs * sizeof(int64_t), cudaMemcpyHostToDevice, stream);
+            cudaMemcpyAsync(dmap + num_pairs, dst_blocks, num_pairs * sizeof(int64_t), cudaMemcpyHostToDevice, stream);
+            static thread_local int attr_dev = -1;
+            const DeviceInfo &di = current_device_info();
+            if (attr_dev != di.ordinal) {
+                cudaFuncSetAttribute(swap_blocks_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kRing * kPieceBytes);
+                attr_dev = di.ordinal;
+            }
+            char *d = static_cast<char *>(kind == 2 ? pa.devicePointer : dst_base);
+            const char *sp = static_cast<const char *>(kind == 1 ? pa.devicePointer : src_base);
+            swap_blocks_bulk_kernel<<<static_cast<unsigned>(num_pairs), 32, kRing * kPieceBytes, stream>>>(
+                d, sp, dmap, dmap + num_pairs, block_bytes);
+            note_launch();
+            check_launch("swap_blocks_batched (mapped host memory)");
+            return;
+        }
+    }
+    // Pageable host memory: merge runs of consecutive (src, dst) blocks into single async copies.
     std::vector<std::pair<int64_t, int64_t>> pairs(num_pairs);
     for (int64_t i = 0; i < num_pairs; ++i) pairs[i] = {src_blocks[i], dst_blocks[i]};
     std::sort(pairs.begin(), pairs.end());

@@ -113,6 +113,21 @@ def test_swap_blocks(direction, dtype):
         assert torch.equal(dst[d].cpu(), before[d].cpu())
 
 
+def test_swap_blocks_pageable_host_memory():
+    """Unpinned host tensors (what candle's CPU storage is, ops.rs:158-164) take the memcpy path."""
+    NB, BS, H, D = 10, 16, 2, 64
+    gpu = randn_t((NB, BS, H, D), 50, torch.bfloat16, DEV)
+    cpu = torch.zeros((NB, BS, H, D), dtype=torch.bfloat16)
+    assert not cpu.is_pinned()
+    ops.swap_blocks(gpu, cpu, {0: 3, 1: 4, 2: 5, 7: 0})
+    for s_, d_ in {0: 3, 1: 4, 2: 5, 7: 0}.items():
+        assert torch.equal(cpu[d_], gpu[s_].cpu())
+    back = torch.zeros_like(gpu)
+    ops.swap_blocks(cpu, back, {3: 9, 4: 8})
+    torch.cuda.synchronize()
+    assert torch.equal(back[9], gpu[0]) and torch.equal(back[8], gpu[1])
+
+
 def test_swap_round_trip_full_sequence():
     """Swap one 4096-token sequence (256 blocks, Llama-3.1-8B geometry) out to pinned host memory and
     back into different blocks: encode -> erase -> decode round trip, byte exact."""
