@@ -30,7 +30,7 @@ constexpr int kBlockK = 64;       // k elements per stage: 128 bytes, one swizzl
 constexpr int kUmmaK = 16;        // k per tcgen05.mma (16-bit inputs)
 constexpr int kGemmThreads = 192;
 constexpr int kEpiThreads = 128;
-constexpr int kMaxTPad = 128;
+constexpr int kMaxTPad = 256;     // activation rows per tile (UMMA N); larger T is cut into chunks
 constexpr int kMaxStages = 12;
 constexpr int kGemmMaxCtas = 256;
 constexpr int kWBytes = kTileN * kBlockK * 2;  // 16 KiB
@@ -41,7 +41,8 @@ struct GemmArgs {
     int T, N, K;
     int t_pad;        // T rounded up to a multiple of 16
     int kb_per_tile;  // ceil(K / 64)
-    int tiles;        // ceil(N / 128)
+    int tiles;        // ceil(N / 128) * t_chunks; tile = n_tile * t_chunks + t_chunk
+    int t_chunks;     // ceil(T / t_pad)
     int stages;
     int tmem_cols;    // power of two >= 2 * t_pad
     int is_bf16;
@@ -110,6 +111,9 @@ gemm_tn_stream_kernel(const __grid_constant__ CUtensorMap map_w,
         // ============================ TMA producer ============================
         if (lane == 0) {
             pdl_launch_dependents();
+            // W is read once when there is a single activation chunk (decode): evict-first.  With
+            // several chunks every weight tile is re-read from L2 once per chunk: keep it.
+            const uint64_t w_policy = a.t_chunks == 1 ? kL2EvictFirst : kL2EvictLast;
             int stage = 0;
             uint32_t phase = 0;
             long long u = u_begin;
@@ -122,14 +126,15 @@ gemm_tn_stream_kernel(const __grid_constant__ CUtensorMap map_w,
                     const long long uu = u_begin + i;
                     const int tile = static_cast<int>(uu / KB), kb = static_cast<int>(uu % KB);
                     mbar_arrive_expect_tx(&full[i], stage_bytes);
-                    tma_load_2d(tiles + i * stage_bytes, &map_w, &full[i], kb * kBlockK, tile * kTileN, kL2EvictFirst);
+                    tma_load_2d(tiles + i * stage_bytes, &map_w, &full[i], kb * kBlockK, (tile / a.t_chunks) * kTileN, w_policy);
                 }
             }
             pdl_wait();
             if (a.trace) a.trace[blockIdx.x * 4 + 0] = t_start;
             for (int i = 0; i < pre; ++i) {
-                const int kb = static_cast<int>((u_begin + i) % KB);
-                tma_load_2d(tiles + i * stage_bytes + kWBytes, &map_x, &full[i], kb * kBlockK, 0, kL2EvictLast);
+                const int tile = static_cast<int>((u_begin + i) / KB), kb = static_cast<int>((u_begin + i) % KB);
+                tma_load_2d(tiles + i * stage_bytes + kWBytes, &map_x, &full[i], kb * kBlockK,
+                            (tile % a.t_chunks) * a.t_pad, kL2EvictLast);
             }
             u += pre;
             stage = pre % a.stages;
@@ -140,8 +145,8 @@ gemm_tn_stream_kernel(const __grid_constant__ CUtensorMap map_w,
                 unsigned char *ws = tiles + stage * stage_bytes;
                 mbar_arrive_expect_tx(&full[stage], stage_bytes);
                 // W is read exactly once: evict-first; x is re-read by every CTA: keep it in L2.
-                tma_load_2d(ws, &map_w, &full[stage], kb * kBlockK, tile * kTileN, kL2EvictFirst);
-                tma_load_2d(ws + kWBytes, &map_x, &full[stage], kb * kBlockK, 0, kL2EvictLast);
+                tma_load_2d(ws, &map_w, &full[stage], kb * kBlockK, (tile / a.t_chunks) * kTileN, w_policy);
+                tma_load_2d(ws + kWBytes, &map_x, &full[stage], kb * kBlockK, (tile % a.t_chunks) * a.t_pad, kL2EvictLast);
                 if (++stage == a.stages) {
                     stage = 0;
                     phase ^= 1;
@@ -201,7 +206,8 @@ gemm_tn_stream_kernel(const __grid_constant__ CUtensorMap map_w,
             const int n = static_cast<int>(min(static_cast<long long>(KB - k0), u_end - u));
             const int buf = seg & 1;
             const bool whole = (n == KB);
-            const int ncol = tile * kTileN + row;  // output column (weight row)
+            const int n_tile = tile / a.t_chunks, t_base = (tile % a.t_chunks) * a.t_pad;
+            const int ncol = n_tile * kTileN + row;  // output column (weight row)
             const int slot = (u == u_begin) ? 0 : 1;
             float *part = a.ws + (static_cast<int64_t>(cta) * 2 + slot) * (a.t_pad * kTileN);
 
@@ -216,7 +222,7 @@ gemm_tn_stream_kernel(const __grid_constant__ CUtensorMap map_w,
                     if (ncol < a.N) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const int t = c * 16 + j;
+                            const int t = t_base + c * 16 + j;
                             if (t < a.T) {
                                 const float f = __uint_as_float(v[j]);
                                 if (a.is_bf16) yb[static_cast<int64_t>(t) * a.ldy + ncol] = __float2bfloat16_rn(f);
@@ -256,7 +262,7 @@ gemm_tn_stream_kernel(const __grid_constant__ CUtensorMap map_w,
                     // Thread (tq, r4) reduces rows r4*4..r4*4+3 of the tile for t = tq, tq+4, ...: 16-byte
                     // loads, 4 t values x 4 partials in flight at a time, partials added in CTA order.
                     const int r4 = etid & 31, tq = etid >> 5;
-                    const int col4 = tile * kTileN + r4 * 4;
+                    const int col4 = n_tile * kTileN + r4 * 4;
                     const bool vec_ok = (a.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 7) == 0) &&
                                         (col4 + 3 < a.N);
                     for (int j0 = 0; j0 < a.t_pad / 4; j0 += 4) {
@@ -290,8 +296,8 @@ gemm_tn_stream_kernel(const __grid_constant__ CUtensorMap map_w,
                         }
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) {
-                            const int t = tq + 4 * (j0 + jj);
-                            if (t >= a.T) continue;
+                            const int t = t_base + tq + 4 * (j0 + jj);
+                            if (t >= a.T || tq + 4 * (j0 + jj) >= a.t_pad) continue;
                             const int64_t o = static_cast<int64_t>(t) * a.ldy + col4;
                             const float f[4] = {acc[jj].x, acc[jj].y, acc[jj].z, acc[jj].w};
                             if (vec_ok) {
@@ -380,9 +386,10 @@ bool launch_stream_gemm(const void *x, const void *w, void *y, int T, int64_t N,
     const DeviceInfo &di = current_device_info();
     GemmArgs a;
     a.y = y; a.ldy = ldy; a.T = T; a.N = static_cast<int>(N); a.K = static_cast<int>(K);
-    a.t_pad = (T + 15) / 16 * 16;
+    a.t_pad = T > kMaxTPad ? kMaxTPad : (T + 15) / 16 * 16;
+    a.t_chunks = (T + a.t_pad - 1) / a.t_pad;
     a.kb_per_tile = static_cast<int>((K + kBlockK - 1) / kBlockK);
-    a.tiles = static_cast<int>((N + kTileN - 1) / kTileN);
+    a.tiles = static_cast<int>((N + kTileN - 1) / kTileN) * a.t_chunks;
     a.is_bf16 = is_bf16 ? 1 : 0;
     int cols = 32;
     while (cols < 2 * a.t_pad) cols <<= 1;
@@ -451,15 +458,11 @@ bool launch_gemm_bf16_tn(const void *x, const void *w, void *y, int64_t T, int64
                    di.cc_minor);
         return false;
     }
-    // Rows are processed in chunks of up to 128 (the N operand of the MMA).  The large-T (prefill)
-    // kernel with 128x256 2-CTA tiles replaces this loop for T > 128.
-    const char *xb = static_cast<const char *>(x);
-    char *yb = static_cast<char *>(y);
-    for (int64_t t0 = 0; t0 < T; t0 += kMaxTPad) {
-        const int tc = static_cast<int>(std::min<int64_t>(kMaxTPad, T - t0));
-        if (!launch_stream_gemm(xb + t0 * ldx * 2, w, yb + t0 * ldy * 2, tc, N, K, ldx, ldw, ldy, true, stream))
-            return false;
+    if (T > (1 << 24)) {
+        set_status(kErrUnsupported, "atoma_gemm_bf16_tn: T = %lld", static_cast<long long>(T));
+        return false;
     }
+    if (!launch_stream_gemm(x, w, y, static_cast<int>(T), N, K, ldx, ldw, ldy, true, stream)) return false;
     return true;
 }
 

@@ -14,8 +14,10 @@ from atoma_infer_b200 import ops  # noqa: E402
 def main():
     dev = "cuda:0"
     out = []
-    for (T, N, K) in [(32, 6144, 4096), (32, 4096, 4096), (1, 3072, 2048), (16, 1280, 8192), (16, 8192, 1024)]:
-        nrot = 16
+    shapes = [(32, 6144, 4096), (32, 4096, 4096), (1, 3072, 2048), (16, 1280, 8192), (16, 8192, 1024),
+              (8192, 6144, 4096), (8192, 4096, 4096), (2048, 6144, 4096)]
+    for (T, N, K) in shapes:
+        nrot = 16 if T <= 256 else 2
         ws = [torch.randn((N, K), device=dev).to(torch.bfloat16) for _ in range(nrot)]
         x = torch.randn((T, K), device=dev).to(torch.bfloat16)
         y = torch.empty((T, N), device=dev, dtype=torch.bfloat16)
@@ -45,8 +47,10 @@ def main():
         t_ours = time_it(lambda i: ops.gemm_bf16_tn(x, ws[i % nrot], out=y))
         t_cublas = time_it(lambda i: torch.matmul(x, ws[i % nrot].t(), out=y))
         byts = 2 * (N * K + T * K + T * N)
+        flops = 2.0 * T * N * K
         out.append({"T": T, "N": N, "K": K, "ours_us": t_ours, "cublas_us": t_cublas,
-                    "ours_GBps": byts / t_ours / 1e3, "cublas_GBps": byts / t_cublas / 1e3})
+                    "ours_GBps": byts / t_ours / 1e3, "cublas_GBps": byts / t_cublas / 1e3,
+                    "ours_TFLOPs": flops / t_ours / 1e6, "cublas_TFLOPs": flops / t_cublas / 1e6})
         print(json.dumps(out[-1]), flush=True)
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / "microbench_gemm.json").write_text(json.dumps(out, indent=1))

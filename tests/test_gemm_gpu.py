@@ -40,7 +40,9 @@ def _check(x, w, y, what):
     (16, 8192, 1024),    # ... and its o_proj (row parallel)
     (128, 1024, 512),
     (5, 1000, 520),      # N not a multiple of 128, K not a multiple of 64
-    (200, 256, 192),     # more than one 128-row chunk
+    (200, 256, 192),
+    (600, 512, 1024),    # three activation chunks (256 + 256 + 88) in one launch
+    (1000, 384, 320),    # ragged everywhere: T, N % 128, K % 64
 ])
 def test_gemm_vs_fp64(T, N, K):
     x = randn_t((T, K), 1, torch.bfloat16, DEV)
