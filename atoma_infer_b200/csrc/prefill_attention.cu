@@ -32,10 +32,12 @@
 namespace atoma {
 namespace {
 
-constexpr int kPfThreads = 192;  // warp 0: loads, warp 1: MMA issue + TMEM alloc, warps 2-5: softmax
+constexpr int kPfThreads = 384;  // warpgroup 0: loads (warp 0) + MMA issue (warp 1); warpgroups 1, 2: softmax
 constexpr int kPfM = 128, kPfN = 128;
+constexpr int kQTiles = 2;       // two 128-row query tiles per CTA, one softmax warpgroup each
 constexpr int kKvStages = 2;
-constexpr int kTmemS0 = 0, kTmemS1 = 128, kTmemO = 256, kTmemCols = 512;
+constexpr int kTmemCols = 512;   // S_A 0..127 | S_B 128..255 | O_A 256.. | O_B 384..
+constexpr int kPfIssueRegs = 56, kPfSoftmaxRegs = 224;  // setmaxnreg: 168 * 384 = 56 * 128 + 224 * 256
 constexpr float kRescaleThreshold = 8.f;  // log2 units: P <= 2^8 between corrections
 
 template <int D>
@@ -43,7 +45,7 @@ struct PfCfg {
     static constexpr int kHalves = D / 64;
     static constexpr int kHalfBytes = 128 * 128;            // 128 rows of 128 bytes
     static constexpr int kTileBytes = kHalves * kHalfBytes;  // one Q / K / V tile
-    static constexpr int kSmem = kTileBytes * (1 + 2 * kKvStages) + 1024;
+    static constexpr int kSmem = kTileBytes * (kQTiles + 2 * kKvStages) + 1024;
 };
 
 struct PfSeq {
@@ -80,11 +82,11 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     using C = PfCfg<D>;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *tiles = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-    unsigned char *sq = tiles;
-    unsigned char *sk = sq + C::kTileBytes;              // [stage]
-    unsigned char *sv = sk + kKvStages * C::kTileBytes;  // [stage]
-    __shared__ __align__(8) uint64_t q_full, k_full[kKvStages], k_empty[kKvStages], v_full[kKvStages],
-        v_empty[kKvStages], s_full[2], p_full[2], pv_done;
+    unsigned char *sq = tiles;                            // [q tile]
+    unsigned char *sk = sq + kQTiles * C::kTileBytes;     // [stage]
+    unsigned char *sv = sk + kKvStages * C::kTileBytes;   // [stage]
+    __shared__ __align__(8) uint64_t q_full[kQTiles], k_full[kKvStages], k_empty[kKvStages], v_full[kKvStages],
+        v_empty[kKvStages], s_full[kQTiles], p_full[kQTiles], pv_done[kQTiles];
     __shared__ uint32_t tmem_base_smem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -92,18 +94,18 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     const int head = blockIdx.y, bidb = blockIdx.z;
 
     if (tid == 0) {
-        mbar_init(&q_full, 1);
         for (int i = 0; i < kKvStages; ++i) {
             mbar_init(&k_full[i], 1);
             mbar_init(&k_empty[i], 1);
             mbar_init(&v_full[i], 1);
             mbar_init(&v_empty[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kQTiles; ++i) {
+            mbar_init(&q_full[i], 1);
             mbar_init(&s_full[i], 1);
             mbar_init(&p_full[i], 4);  // one arrival per softmax warp
+            mbar_init(&pv_done[i], 1);
         }
-        mbar_init(&pv_done, 1);
         fence_mbar_init();
         tma_prefetch_desc(&map_q);
         tma_prefetch_desc(&map_k);
@@ -118,21 +120,28 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     pdl_wait();
 
     const PfSeq si = pf_seq(p, bidb);
-    const int m0 = m_block * kPfM;
     const int len_q = si.len_q, len_k = si.len_k;
     const int shift = len_k - len_q;  // mask.h:171-172: key j visible to query i iff j <= i + shift
-    int n_tiles = 0;
-    if (m0 < len_q) {
-        n_tiles = (len_k + kPfN - 1) / kPfN;
-        if (p.is_causal) {
-            const int lim = min(m0 + kPfM, len_q) + shift;  // one past the last visible key of the tile
-            n_tiles = min(n_tiles, lim <= 0 ? 0 : (lim + kPfN - 1) / kPfN);
+    // Query tile t of this CTA covers rows m0[t] .. m0[t] + 127 and needs the first nt[t] key tiles.
+    int m0[kQTiles], nt[kQTiles];
+#pragma unroll
+    for (int t = 0; t < kQTiles; ++t) {
+        m0[t] = (m_block * kQTiles + t) * kPfM;
+        nt[t] = 0;
+        if (m0[t] < len_q) {
+            nt[t] = (len_k + kPfN - 1) / kPfN;
+            if (p.is_causal) {
+                const int lim = min(m0[t] + kPfM, len_q) + shift;  // one past the last visible key of the tile
+                nt[t] = min(nt[t], lim <= 0 ? 0 : (lim + kPfN - 1) / kPfN);
+            }
         }
     }
+    const int n_max = max(nt[0], nt[1]);
     const int kvh = head / (p.h / p.h_k);  // flash_fwd_kernel.h:593
 
-    if (m0 < len_q && n_tiles > 0) {
-        if (warp == 0) {
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kPfIssueRegs));
+        if (warp == 0 && n_max > 0) {
             // ================================ loads ================================
             // A tile that lies completely inside its sequence is one TMA transaction (kHalves boxes);
             // a ragged one is filled with cp.async + zero fill in the same 128-byte-swizzled layout.
@@ -164,8 +173,12 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             const T *qg = static_cast<const T *>(p.q) + si.q_off + static_cast<int64_t>(head) * p.q_hs;
             const T *kg = static_cast<const T *>(p.k) + si.k_off + static_cast<int64_t>(kvh) * p.k_hs;
             const T *vg = static_cast<const T *>(p.v) + si.v_off + static_cast<int64_t>(kvh) * p.v_hs;
-            load_tile(sq, &map_q, &q_full, qg, p.q_rs, m0, len_q, si.q_row0 + m0, head, si.q_batch, kL2EvictFirst);
-            for (int j = 0; j < n_tiles; ++j) {
+#pragma unroll
+            for (int t = 0; t < kQTiles; ++t)
+                if (nt[t] > 0)
+                    load_tile(sq + t * C::kTileBytes, &map_q, &q_full[t], qg, p.q_rs, m0[t], len_q, si.q_row0 + m0[t],
+                              head, si.q_batch, kL2EvictFirst);
+            for (int j = 0; j < n_max; ++j) {
                 const int s = j % kKvStages;
                 const uint32_t par = ((j / kKvStages) & 1) ^ 1;
                 mbar_wait(&k_empty[s], par);
@@ -175,59 +188,97 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 load_tile(sv + s * C::kTileBytes, &map_v, &v_full[s], vg, p.v_rs, j * kPfN, len_k,
                           si.k_row0 + j * kPfN, kvh, si.k_batch, kL2EvictLast);
             }
-        } else if (warp == 1) {
+        } else if (warp == 1 && lane == 0 && n_max > 0) {
             // ================================ MMA issue ================================
-            if (lane == 0) {
-                constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
-                const uint32_t idesc_qk = umma_idesc_f16(kPfM, kPfN, kBf16, false);
-                const uint32_t idesc_pv = umma_idesc_f16(kPfM, D, kBf16, true);
-                const uint32_t q_addr = smem_u32(sq);
-                auto issue_qk = [&](int j) {
-                    const int s = j % kKvStages;
-                    mbar_wait(&k_full[s], (j / kKvStages) & 1);
-                    tc_fence_after_sync();
-                    const uint32_t k_addr = smem_u32(sk + s * C::kTileBytes);
-                    const uint32_t tmem_s = tmem_base + ((j & 1) ? kTmemS1 : kTmemS0);
+            // Order per key tile j:  P.V(A,j)  QK(A,j+1)  P.V(B,j)  QK(B,j+1)
+            // so while one query tile is being exponentiated the tensor pipe works for the other.
+            constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
+            const uint32_t idesc_qk = umma_idesc_f16(kPfM, kPfN, kBf16, false);
+            const uint32_t idesc_pv = umma_idesc_f16(kPfM, D, kBf16, true);
+            auto issue_qk = [&](int t, int j) {
+                const int s = j % kKvStages;
+                const uint32_t q_addr = smem_u32(sq + t * C::kTileBytes);
+                const uint32_t k_addr = smem_u32(sk + s * C::kTileBytes);
+                const uint32_t tmem_s = tmem_base + t * 128;
 #pragma unroll
-                    for (int kk = 0; kk < D / 16; ++kk) {
-                        const uint32_t off = (kk >> 2) * C::kHalfBytes + (kk & 3) * 32;
-                        umma_f16_ss(tmem_s, umma_desc_k_sw128(q_addr + off), umma_desc_k_sw128(k_addr + off),
-                                    idesc_qk, kk != 0 ? 1u : 0u);
-                    }
-                    umma_commit(&k_empty[s]);
-                    umma_commit(&s_full[j & 1]);
-                };
-                mbar_wait(&q_full, 0);
-                issue_qk(0);
-                for (int j = 0; j < n_tiles; ++j) {
-                    if (j + 1 < n_tiles) issue_qk(j + 1);
-                    const int s = j % kKvStages;
-                    mbar_wait(&v_full[s], (j / kKvStages) & 1);
-                    mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-                    tc_fence_after_sync();
-                    const uint32_t v_addr = smem_u32(sv + s * C::kTileBytes);
-                    const uint32_t tmem_p = tmem_base + ((j & 1) ? kTmemS1 : kTmemS0);
+                for (int kk = 0; kk < D / 16; ++kk) {
+                    const uint32_t off = (kk >> 2) * C::kHalfBytes + (kk & 3) * 32;
+                    umma_f16_ss(tmem_s, umma_desc_k_sw128(q_addr + off), umma_desc_k_sw128(k_addr + off), idesc_qk,
+                                kk != 0 ? 1u : 0u);
+                }
+                umma_commit(&s_full[t]);
+            };
+            auto issue_pv = [&](int t, int j) {
+                const int s = j % kKvStages;
+                const uint32_t v_addr = smem_u32(sv + s * C::kTileBytes);
+                const uint32_t tmem_p = tmem_base + t * 128;
+                const uint32_t tmem_o = tmem_base + 256 + t * 128;
 #pragma unroll
-                    for (int kk = 0; kk < kPfN / 16; ++kk) {
-                        // 16 keys = 16 rows of 128 bytes of V; 16 P values = 8 packed 32-bit columns
-                        umma_f16_ts(tmem_base + kTmemO, tmem_p + kk * 8,
-                                    umma_desc_mn_sw128(v_addr + kk * 16 * 128, C::kHalfBytes), idesc_pv,
-                                    (j | kk) != 0 ? 1u : 0u);
-                    }
-                    umma_commit(&v_empty[s]);
-                    umma_commit(&pv_done);
+                for (int kk = 0; kk < kPfN / 16; ++kk) {
+                    // 16 keys = 16 rows of 128 bytes of V; 16 P values = 8 packed 32-bit columns
+                    umma_f16_ts(tmem_o, tmem_p + kk * 8, umma_desc_mn_sw128(v_addr + kk * 16 * 128, C::kHalfBytes),
+                                idesc_pv, (j | kk) != 0 ? 1u : 0u);
+                }
+                umma_commit(&pv_done[t]);
+            };
+            // first key tile: both query tiles
+            mbar_wait(&k_full[0], 0);
+#pragma unroll
+            for (int t = 0; t < kQTiles; ++t) {
+                if (nt[t] > 0) {
+                    mbar_wait(&q_full[t], 0);
+                    tc_fence_after_sync();
+                    issue_qk(t, 0);
                 }
             }
-        } else {
-            // ================================ softmax / epilogue ================================
-            const int quad = warp & 3;
-            const int row = quad * 32 + lane;   // query row of this thread within the tile
-            const int grow = m0 + row;          // ... within the sequence
-            const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+            umma_commit(&k_empty[0]);
+            for (int j = 0; j < n_max; ++j) {
+                const int s = j % kKvStages, sn = (j + 1) % kKvStages;
+                mbar_wait(&v_full[s], (j / kKvStages) & 1);
+                bool k_next_ready = false;
+#pragma unroll
+                for (int t = 0; t < kQTiles; ++t) {
+                    if (j < nt[t]) {
+                        mbar_wait(&p_full[t], j & 1);
+                        tc_fence_after_sync();
+                        issue_pv(t, j);
+                    }
+                    if (j + 1 < nt[t]) {
+                        if (!k_next_ready) {
+                            mbar_wait(&k_full[sn], ((j + 1) / kKvStages) & 1);
+                            k_next_ready = true;
+                        }
+                        tc_fence_after_sync();
+                        issue_qk(t, j + 1);
+                    }
+                }
+                umma_commit(&v_empty[s]);                       // both P.V of tile j are issued
+                if (k_next_ready) umma_commit(&k_empty[sn]);    // ... and every QK^T of tile j + 1
+            }
+        }
+    } else {
+        // ================================ softmax / epilogue warpgroups ================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kPfSoftmaxRegs));
+        const int t = (warp >> 2) - 1;          // query tile of this warpgroup
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;       // query row of this thread within the tile
+        const int m0t = t ? m0[1] : m0[0];
+        const int grow = m0t + row;             // ... within the sequence
+        const int n_tiles = t ? nt[1] : nt[0];
+        const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+        const uint32_t tmem_s = tmem_base + lane_addr + t * 128;
+        const uint32_t tmem_o = tmem_base + lane_addr + 256 + t * 128;
+        T *og = static_cast<T *>(p.o) + si.o_off + static_cast<int64_t>(head) * p.o_hs +
+                static_cast<int64_t>(grow) * p.o_rs;
+        int64_t lse_idx = 0;
+        if (p.lse && grow < len_q) {
+            if (p.unpadded_lse && p.cu_q) lse_idx = static_cast<int64_t>(head) * p.cu_q[p.b] + si.q_start + grow;
+            else lse_idx = (static_cast<int64_t>(bidb) * p.h + head) * p.seqlen_q + grow;
+        }
+        if (n_tiles > 0) {
             float m_ref = -INFINITY, l_run = 0.f;
             for (int j = 0; j < n_tiles; ++j) {
-                const uint32_t tmem_s = tmem_base + lane_addr + ((j & 1) ? kTmemS1 : kTmemS0);
-                mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+                mbar_wait(&s_full[t], j & 1);
                 tc_fence_after_sync();
                 uint32_t sv_[128];
 #pragma unroll
@@ -236,16 +287,21 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 // ---- masks: only tiles that touch the sequence end or the causal diagonal ----
                 const int col0 = j * kPfN;
                 const bool tail = col0 + kPfN > len_k;
-                const bool diag = p.is_causal && (col0 + kPfN - 1 > m0 + shift);
+                const bool diag = p.is_causal && (col0 + kPfN - 1 > m0t + shift);
                 if (tail || diag) {
                     const int lim = p.is_causal ? min(len_k, grow + shift + 1) : len_k;  // first masked column
 #pragma unroll
                     for (int c = 0; c < 128; ++c)
                         if (col0 + c >= lim) sv_[c] = 0xff800000u;  // -inf
                 }
-                float mx = -INFINITY;
+                // eight independent chains: a single running max / sum is 128 dependent operations
+                float mx8[8];
 #pragma unroll
-                for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(sv_[c]));
+                for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(sv_[i]);
+#pragma unroll
+                for (int c = 8; c < 128; ++c) mx8[c & 7] = fmaxf(mx8[c & 7], __uint_as_float(sv_[c]));
+                const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                                       fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
                 const float m_tile = mx * p.scale_log2;  // scale_log2 > 0 (checked on the host)
                 // ---- lazy running maximum ----
                 const bool need = m_tile > m_ref + kRescaleThreshold;  // also the first finite tile (m_ref = -inf)
@@ -256,22 +312,23 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     if (j > 0) {
                         // O of this row lives in tensor memory: wait until P.V of the previous tile has
                         // been accumulated, rescale, write back.  Rare after the first tiles.
-                        mbar_wait(&pv_done, (j - 1) & 1);
+                        mbar_wait(&pv_done[t], (j - 1) & 1);
                         tc_fence_after_sync();
 #pragma unroll
                         for (int c = 0; c < D / 32; ++c) {
                             uint32_t ov[32];
-                            tmem_ld_32x32b_x32(tmem_base + lane_addr + kTmemO + c * 32, ov);
+                            tmem_ld_32x32b_x32(tmem_o + c * 32, ov);
                             tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-                            tmem_st_32x32b_x32(tmem_base + lane_addr + kTmemO + c * 32, ov);
+                            tmem_st_32x32b_x32(tmem_o + c * 32, ov);
                         }
                         tmem_st_wait();
                     }
                 }
                 const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
                 // ---- P = exp2(S * scale - m), row sum, packed 16-bit pairs back over S ----
+                float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t pk[16];
@@ -279,27 +336,26 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     for (int i = 0; i < 16; ++i) {
                         const float p0 = fast_exp2(fmaf(__uint_as_float(sv_[c * 32 + 2 * i]), p.scale_log2, -m_use));
                         const float p1 = fast_exp2(fmaf(__uint_as_float(sv_[c * 32 + 2 * i + 1]), p.scale_log2, -m_use));
-                        l_run += p0 + p1;
+                        ls[i & 3] += p0 + p1;
                         pk[i] = pack2<T>(p0, p1);
                     }
                     tmem_st_32x32b_x16(tmem_s + c * 16, pk);
                 }
+                l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
                 tmem_st_wait();
                 tc_fence_before_sync();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&p_full[j & 1]);
+                if (lane == 0) mbar_arrive(&p_full[t]);
             }
             // ---- epilogue: O / rowsum -> global ----
-            mbar_wait(&pv_done, (n_tiles - 1) & 1);
+            mbar_wait(&pv_done[t], (n_tiles - 1) & 1);
             tc_fence_after_sync();
             const bool empty = (l_run == 0.f || l_run != l_run);
             const float inv = empty ? 0.f : 1.f / l_run;
-            T *og = static_cast<T *>(p.o) + si.o_off + static_cast<int64_t>(head) * p.o_hs +
-                    static_cast<int64_t>(grow) * p.o_rs;
 #pragma unroll
             for (int c = 0; c < D / 32; ++c) {
                 uint32_t ov[32];
-                tmem_ld_32x32b_x32(tmem_base + lane_addr + kTmemO + c * 32, ov);
+                tmem_ld_32x32b_x32(tmem_o + c * 32, ov);
                 tmem_ld_wait();
                 if (grow < len_q) {
 #pragma unroll
@@ -313,27 +369,13 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     }
                 }
             }
-            if (p.lse && grow < len_q) {
-                int64_t idx;
-                if (p.unpadded_lse && p.cu_q) idx = static_cast<int64_t>(head) * p.cu_q[p.b] + si.q_start + grow;
-                else idx = (static_cast<int64_t>(bidb) * p.h + head) * p.seqlen_q + grow;
-                p.lse[idx] = empty ? INFINITY : m_ref * 0.6931471805599453f + __logf(l_run);
-            }
-        }
-    } else if (m0 < len_q && warp >= 2) {
-        // No visible key for any row of this tile: O = 0, LSE = +inf (flash_fwd_kernel.h:543-582).
-        const int grow = m0 + (warp & 3) * 32 + lane;
-        if (grow < len_q) {
-            T *og = static_cast<T *>(p.o) + si.o_off + static_cast<int64_t>(head) * p.o_hs +
-                    static_cast<int64_t>(grow) * p.o_rs;
+            if (p.lse && grow < len_q)
+                p.lse[lse_idx] = empty ? INFINITY : m_ref * 0.6931471805599453f + __logf(l_run);
+        } else if (grow < len_q) {
+            // No visible key for any row of this tile: O = 0, LSE = +inf (flash_fwd_kernel.h:543-582).
 #pragma unroll
             for (int c = 0; c < D / 8; ++c) *reinterpret_cast<uint4 *>(og + c * 8) = make_uint4(0, 0, 0, 0);
-            if (p.lse) {
-                int64_t idx;
-                if (p.unpadded_lse && p.cu_q) idx = static_cast<int64_t>(head) * p.cu_q[p.b] + si.q_start + grow;
-                else idx = (static_cast<int64_t>(bidb) * p.h + head) * p.seqlen_q + grow;
-                p.lse[idx] = INFINITY;
-            }
+            if (p.lse) p.lse[lse_idx] = INFINITY;
         }
     }
 
@@ -403,7 +445,7 @@ bool launch_prefill(const CUtensorMap &mq, const CUtensorMap &mk, const CUtensor
         }
         attr_dev = di.ordinal;
     }
-    dim3 grid((p.seqlen_q + kPfM - 1) / kPfM, p.h, p.b);
+    dim3 grid((p.seqlen_q + kQTiles * kPfM - 1) / (kQTiles * kPfM), p.h, p.b);
     prefill_attn_kernel<T, D><<<grid, kPfThreads, smem, stream>>>(mq, mk, mv, p);
     note_launch();
     return check_launch("prefill_attn_kernel");
