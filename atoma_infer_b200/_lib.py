@@ -128,6 +128,7 @@ SIGNATURES = {
     "reshape_and_cache_flash": (None, [C.c_void_p] * 5 + [C.c_int64] * 7 + [C.c_uint32, C.c_void_p]),
     # part 2 (extensions)
     "run_mha_stream": (None, _RUN_MHA_ARGS + [C.c_void_p]),
+    "atoma_rope_reshape_and_cache": (None, [C.c_void_p] * 9 + [C.c_int64] * 10 + [C.c_uint32, C.c_void_p]),
     "swap_blocks_batched": (None, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                    C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
     "atoma_gemm_bf16_tn": (None, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int64] * 6 + [C.c_void_p]),

@@ -224,6 +224,69 @@ __global__ void reshape_and_cache_flash_scalar_kernel(
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fused rotary embedding + cache write
+// ---------------------------------------------------------------------------------------------
+// What the reference does with two index_select, two rope kernels, four transpose+contiguous copies
+// and reshape_and_cache_flash (models/src/llama.rs:218-251, 269-304; flash_attention.rs:361) in one
+// pass: q and k are rotated in place (non-interleaved "rotate half": out[:d/2] = x1 cos - x2 sin,
+// out[d/2:] = x1 sin + x2 cos, cos/sin rows selected by the token's position), the rotated k and
+// the untouched v go to their cache slot.  fp32 arithmetic, one rounding to the io type.
+// One CTA per token; a work item = 8 elements of each half of one head (two 16-byte accesses).
+template <typename T>
+__global__ void __launch_bounds__(256)
+rope_reshape_and_cache_kernel(T *__restrict__ q, T *__restrict__ k, const T *__restrict__ v,
+                              T *__restrict__ k_cache, T *__restrict__ v_cache,
+                              const int64_t *__restrict__ positions, const T *__restrict__ cos_t,
+                              const T *__restrict__ sin_t, const int64_t *__restrict__ slot_mapping,
+                              int num_heads, int num_kv_heads, int head_size, int64_t q_stride,
+                              int64_t k_stride, int64_t v_stride, int64_t rot_stride, int64_t block_stride,
+                              int64_t block_size) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t token = blockIdx.x;
+    const int half = head_size / 2, cph = half / 8;  // 16-byte chunks per half head
+    const int64_t pos = positions[token];
+    const int64_t slot = slot_mapping ? slot_mapping[token] : -1;
+    const bool to_cache = slot >= 0;  // slot < 0: padded token (cache_manager.cu:151-155)
+    const int64_t cache_row = to_cache ? (slot / block_size) * block_stride + (slot % block_size) * num_kv_heads * head_size : 0;
+    const T *cr = cos_t + pos * rot_stride, *sr = sin_t + pos * rot_stride;
+    const int q_items = num_heads * cph, k_items = num_kv_heads * cph, v_items = num_kv_heads * head_size / 8;
+    for (int it = threadIdx.x; it < q_items + k_items + v_items; it += blockDim.x) {
+        if (it < q_items + k_items) {
+            const bool is_k = it >= q_items;
+            const int j = is_k ? it - q_items : it;
+            const int h = j / cph, c = j % cph;
+            T *x = (is_k ? k + token * k_stride : q + token * q_stride) + h * head_size + c * 8;
+            const uint4 a = *reinterpret_cast<const uint4 *>(x), b = *reinterpret_cast<const uint4 *>(x + half);
+            const uint4 cw = *reinterpret_cast<const uint4 *>(cr + c * 8), sw = *reinterpret_cast<const uint4 *>(sr + c * 8);
+            const T *x1 = reinterpret_cast<const T *>(&a), *x2 = reinterpret_cast<const T *>(&b);
+            const T *cc = reinterpret_cast<const T *>(&cw), *ss = reinterpret_cast<const T *>(&sw);
+            uint4 o1, o2;
+            T *y1 = reinterpret_cast<T *>(&o1), *y2 = reinterpret_cast<T *>(&o2);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float f1 = static_cast<float>(x1[e]), f2 = static_cast<float>(x2[e]);
+                const float fc = static_cast<float>(cc[e]), fs = static_cast<float>(ss[e]);
+                y1[e] = static_cast<T>(f1 * fc - f2 * fs);
+                y2[e] = static_cast<T>(f1 * fs + f2 * fc);
+            }
+            *reinterpret_cast<uint4 *>(x) = o1;
+            *reinterpret_cast<uint4 *>(x + half) = o2;
+            if (is_k && to_cache) {
+                T *dst = k_cache + cache_row + h * head_size + c * 8;
+                *reinterpret_cast<uint4 *>(dst) = o1;
+                *reinterpret_cast<uint4 *>(dst + half) = o2;
+            }
+        } else if (to_cache) {
+            const int j = it - q_items - k_items;
+            *reinterpret_cast<uint4 *>(v_cache + cache_row + j * 8) =
+                ld_nc_v4(v + token * v_stride + j * 8);
+        }
+    }
+}
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 void copy_blocks_impl(void *key_cache_ptrs, void *value_cache_ptrs, const void *block_mapping,
@@ -329,6 +392,54 @@ extern "C" void reshape_and_cache_flash(void *key, void *value, void *key_cache,
     }
     note_launch();
     check_launch("reshape_and_cache_flash");
+}
+
+extern "C" void atoma_rope_reshape_and_cache(void *q, void *k, void *v, void *key_cache, void *value_cache,
+                                             const int64_t *positions, const void *cos, const void *sin,
+                                             const int64_t *slot_mapping, int64_t num_tokens,
+                                             int64_t num_heads, int64_t num_kv_heads, int64_t head_size,
+                                             int64_t q_stride, int64_t k_stride, int64_t v_stride,
+                                             int64_t rot_stride, int64_t block_stride, int64_t block_size,
+                                             uint32_t dtype, atoma_stream_t stream_) {
+    clear_status();
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (dtype > 1) {
+        set_status(kErrUnsupported, "atoma_rope_reshape_and_cache: dtype %u (0 = f16, 1 = bf16)", dtype);
+        return;
+    }
+    if (num_tokens <= 0) return;
+    const bool ok = head_size > 0 && head_size % 16 == 0 && aligned16(q) && aligned16(k) && aligned16(v) &&
+                    aligned16(key_cache) && aligned16(value_cache) && aligned16(cos) && aligned16(sin) &&
+                    q_stride % 8 == 0 && k_stride % 8 == 0 && v_stride % 8 == 0 && rot_stride % 8 == 0 &&
+                    block_stride % 8 == 0 && num_heads > 0 && num_kv_heads > 0 && positions != nullptr;
+    if (!ok) {
+        set_status(kErrUnsupported,
+                   "atoma_rope_reshape_and_cache: head_size must be a multiple of 16 and all pointers / strides "
+                   "16-byte aligned");
+        return;
+    }
+    cudaError_t e;
+    if (dtype == 1)
+        e = launch_ex(rope_reshape_and_cache_kernel<__nv_bfloat16>, dim3(static_cast<unsigned>(num_tokens)), dim3(256), 0,
+                      stream, static_cast<__nv_bfloat16 *>(q), static_cast<__nv_bfloat16 *>(k),
+                      static_cast<const __nv_bfloat16 *>(v), static_cast<__nv_bfloat16 *>(key_cache),
+                      static_cast<__nv_bfloat16 *>(value_cache), positions, static_cast<const __nv_bfloat16 *>(cos),
+                      static_cast<const __nv_bfloat16 *>(sin), slot_mapping, static_cast<int>(num_heads),
+                      static_cast<int>(num_kv_heads), static_cast<int>(head_size), q_stride, k_stride, v_stride,
+                      rot_stride, block_stride, block_size);
+    else
+        e = launch_ex(rope_reshape_and_cache_kernel<__half>, dim3(static_cast<unsigned>(num_tokens)), dim3(256), 0, stream,
+                      static_cast<__half *>(q), static_cast<__half *>(k), static_cast<const __half *>(v),
+                      static_cast<__half *>(key_cache), static_cast<__half *>(value_cache), positions,
+                      static_cast<const __half *>(cos), static_cast<const __half *>(sin), slot_mapping,
+                      static_cast<int>(num_heads), static_cast<int>(num_kv_heads), static_cast<int>(head_size), q_stride,
+                      k_stride, v_stride, rot_stride, block_stride, block_size);
+    note_launch();
+    if (e != cudaSuccess) {
+        set_status(static_cast<int>(e), "atoma_rope_reshape_and_cache: %s", cudaGetErrorString(e));
+        return;
+    }
+    check_launch("atoma_rope_reshape_and_cache");
 }
 
 extern "C" void swap_blocks_batched(void *dst_base, const void *src_base,

@@ -224,6 +224,42 @@ def reshape_and_cache_flash(key, value, key_cache, value_cache, slot_mapping) ->
     _check(_lib.lib().atoma_reshape_and_cache_flash(*[_ref(d) for d in ds], _stream()))
 
 
+def rope_reshape_and_cache(q, k, v, key_cache, value_cache, positions, cos, sin, slot_mapping=None) -> None:
+    """Fused rotary embedding (in place on q and k) + KV-cache write: what
+    CausalSelfAttention::forward does between the projections and the attention call
+    (models/src/llama.rs:269-304 + flash_attention.rs:361).  q [T, H, D], k/v [T, Hkv, D] with a
+    contiguous [heads, D] tail, positions i64 [T], cos/sin [max_pos, D/2] in the q dtype."""
+    T, H, D = q.shape
+    HK = k.shape[1]
+    if q.dtype not in (torch.float16, torch.bfloat16) or k.dtype != q.dtype or v.dtype != q.dtype:
+        raise AtomaError("Only support f16/bf16 dtypes and q, k, v must have same dtype")
+    if cos.dtype != q.dtype or sin.dtype != q.dtype or cos.shape[-1] != D // 2 or sin.shape != cos.shape:
+        raise AtomaError(f"cos/sin must be [max_pos, {D // 2}] tensors of the query dtype")
+    if positions.dtype != torch.int64 or positions.numel() != T:
+        raise AtomaError(f"input_positions must be of dtype i64 and hold {T} positions")
+    for name, t, heads in (("q", q, H), ("k", k, HK), ("v", v, HK)):
+        if t.stride(2) != 1 or t.stride(1) != D or t.shape[2] != D or t.shape[0] != T:
+            raise AtomaError(f"{name} must be [num_tokens, heads, head_size] with contiguous heads")
+    if v.shape[1] != HK:
+        raise AtomaError("key and value must have the same number of heads")
+    block_stride = block_size = 0
+    kc = vc = sm = None
+    if slot_mapping is not None:
+        if key_cache.shape[2:] != (HK, D) or value_cache.shape != key_cache.shape:
+            raise AtomaError(f"caches must be [num_blocks, block_size, {HK}, {D}]")
+        if key_cache.stride(0) != value_cache.stride(0):
+            raise AtomaError("Only support block_stride == value_cache.stride[0]")
+        block_stride, block_size = key_cache.stride(0), key_cache.shape[1]
+        kc, vc, sm = key_cache.data_ptr(), value_cache.data_ptr(), slot_mapping.data_ptr()
+    L = _lib.lib()
+    L.atoma_rope_reshape_and_cache(q.data_ptr(), k.data_ptr(), v.data_ptr(), kc, vc, positions.data_ptr(),
+                                   cos.data_ptr(), sin.data_ptr(), sm, T, H, HK, D, q.stride(0), k.stride(0),
+                                   v.stride(0), cos.stride(0), block_stride, block_size,
+                                   1 if q.dtype == torch.bfloat16 else 0, _stream())
+    if L.atoma_last_status() != 0:
+        raise AtomaError(L.atoma_last_error().decode())
+
+
 def copy_blocks(key_caches: Sequence[torch.Tensor], value_caches: Sequence[torch.Tensor],
                 block_mapping: torch.Tensor) -> None:
     """cache_manager.rs:148-307 — block_mapping: device i64 [num_pairs, 2]"""

@@ -7,18 +7,21 @@ Workload (config 2 of BASELINE.json): one DECODE STEP of Llama-3.1-8B's attentio
 batch 32, every sequence at context 4096, block_size 16 — for each of the 32 layers
 
     qkv = x . Wqkv^T            (models/src/llama.rs:269-271; one fused-N GEMM)
-    reshape_and_cache_flash     (models/src/flash_attention.rs:361)
+    RoPE on q, k                (llama.rs:218-251, 300-301)        } ours: ONE fused kernel
+    reshape_and_cache_flash     (models/src/flash_attention.rs:361) } (atoma_rope_reshape_and_cache)
     paged decode attention      (flash_attention.rs:455 -> flash_attn_kv_cache_full -> run_mha)
     x = attn . Wo^T             (llama.rs:311)  [+ NCCL all-reduce under tensor parallelism]
 
 with a distinct 541 MB KV cache per layer (17.3 GB in total: every layer's K/V comes from HBM, no
-L2 flush needed).  RoPE, MLP, norms and lm_head are outside SURVEY §8's scope table and not timed;
+L2 flush needed).  MLP, norms and lm_head are outside SURVEY §8's scope table and not timed;
 `config.workload` says so.  Metric: decode tokens/s = batch / step time, whole job.
 
 `--impl ours` runs libflashattention (this repo's sm_100a kernels) through the public operator API
 (atoma_infer_b200.ops); `--impl reference` runs the REFERENCE's own kernels (oracle/_ref, compiled
 from /root/reference/csrc/kernels for sm_100) with the argument tuples its Rust wrappers derive,
-launched eagerly from one host thread on the legacy default stream as the reference does.  The
+launched eagerly from one host thread on the legacy default stream as the reference does (RoPE with
+candle's kernel count — 2 index_select + 2 rope + 4 transpose/contiguous copies per layer — as 8
+element-wise torch kernels in bf16).  The
 reference has no CPU implementation of this path (cpu_fwd bails, csrc/src/lib.rs:1862-1872): its
 "CPU-host-timed" number is host wall-clock around the GPU step, which is what that arm reports.
 Dense GEMMs are cuBLAS (torch.matmul) in the reference arm, as in the reference (candle -> cuBLAS).
@@ -47,7 +50,7 @@ if str(ROOT) not in sys.path:
 L, HIDDEN, H, HK, D, PAGE = 32, 4096, 32, 8, 128, 16
 BATCH, CTX = 32, 4096
 MB = CTX // PAGE  # block-table width
-METRIC = "decode tokens/sec Llama-3.1-8B bf16 b32 ctx4k (attention path: qkv_proj + cache write + paged decode attention + o_proj, 32 layers)"
+METRIC = "decode tokens/sec Llama-3.1-8B bf16 b32 ctx4k (attention path: qkv_proj + RoPE + cache write + paged decode attention + o_proj, 32 layers)"
 
 
 def parse():
@@ -146,9 +149,13 @@ class State:
         last = (lens.long() - 1)
         slots = perm[torch.arange(BATCH), (last // PAGE)].long() * PAGE + last % PAGE  # worker.rs:392-401
         x = (torch.randn((BATCH, HIDDEN), generator=gm, dtype=torch.float32)).to(bf)
+        # rotary tables as the reference builds them (models/src/llama.rs:145-199), positions = len - 1
+        inv = 1.0 / (500000.0 ** (torch.arange(0, D, 2, dtype=torch.float32) / D))
+        ang = torch.arange(CTX + PAGE, dtype=torch.float32)[:, None] * inv[None, :]
+        self.cos, self.sin = ang.cos().to(bf).to(dev), ang.sin().to(bf).to(dev)
         # pinned host copies (the step's inputs) and their device images
         self.host = {"x": x.pin_memory(), "bt": perm.pin_memory(), "lens": lens.pin_memory(),
-                     "slots": slots.pin_memory()}
+                     "slots": slots.pin_memory(), "pos": last.clone().pin_memory()}
         self.devt = {k: v.to(dev) for k, v in self.host.items()}
         self.out = torch.empty((BATCH, HIDDEN), device=dev, dtype=bf)
         self.out_host = torch.empty((BATCH, HIDDEN), dtype=bf).pin_memory()
@@ -186,8 +193,9 @@ def make_step(st: State, impl: str, gemm: str, dist):
         def attn(q, kc, vc, layer):
             return ops.flash_attn_kv_cache_full(q, kc, vc, None, st.scale, d["bt"], d["lens"], True)
 
-        def cache_write(k, v, kc, vc):
-            ops.reshape_and_cache_flash(k, v, kc, vc, d["slots"])
+        def rope_and_cache_write(q, k, v, kc, vc):
+            ops.rope_reshape_and_cache(q, k, v, kc, vc, d["pos"], st.cos, st.sin, d["slots"])
+            return q, k
     else:
         from atoma_infer_b200 import ops  # host planner only: derives the reference's run_mha arguments
         from oracle.ref_lib import RefLib
@@ -203,20 +211,33 @@ def make_step(st: State, impl: str, gemm: str, dist):
                                                 window_size_right=0, num_sms=sms)
             return ref.execute(plan, q, sync=False)
 
-        def cache_write(k, v, kc, vc):
+        # candle runs RoPE as 2 index_select + 2 rope kernels + 4 transpose/contiguous copies per layer
+        # (models/src/llama.rs:238-304).  Same kernel count here, in the model dtype:
+        # rope(x) = x * [cos, cos] + roll(x, d/2) * [-sin, sin]  ->  index_select x2 + (roll, mul, addcmul) x2.
+        cos_full = torch.cat([st.cos, st.cos], dim=-1)
+        sin_signed = torch.cat([-st.sin, st.sin], dim=-1)
+
+        def rope_torch(x, cos, sin):
+            return torch.addcmul(x * cos, torch.roll(x, D // 2, dims=-1), sin)
+
+        def rope_and_cache_write(q, k, v, kc, vc):
+            cos = cos_full.index_select(0, d["pos"])[:, None, :]
+            sin = sin_signed.index_select(0, d["pos"])[:, None, :]
+            q, k = rope_torch(q, cos, sin), rope_torch(k, cos, sin)
             ref.lib.reshape_and_cache_flash(k.data_ptr(), v.data_ptr(), kc.data_ptr(), vc.data_ptr(),
                                             d["slots"].data_ptr(), kc.stride(0), BATCH, st.hk, D, PAGE,
                                             k.stride(0), v.stride(0), 1, stream0)
+            return q, k
 
     def layer(l, x, out=None):
         """One layer of the path on this rank: x [B, hidden] -> partial (pre-all-reduce) o_proj output."""
         qkv = mm(x, st.wqkv[l])                                   # [B, (h + 2 hk) D]
-        q = qkv[:, :nq].unflatten(1, (st.h, D)).unsqueeze(1)      # [B, 1, h, D] (strided view)
+        q = qkv[:, :nq].unflatten(1, (st.h, D))                   # [B, h, D] (strided view)
         k = qkv[:, nq:nq + nkv].unflatten(1, (st.hk, D))          # [B, hk, D]
         v = qkv[:, nq + nkv:].unflatten(1, (st.hk, D))
         kc, vc = st.kv[l][0], st.kv[l][1]
-        cache_write(k, v, kc, vc)
-        o = attn(q, kc, vc, l)                                    # [B, 1, h, D]
+        q, k = rope_and_cache_write(q, k, v, kc, vc)
+        o = attn(q.unsqueeze(1), kc, vc, l)                       # [B, 1, h, D]
         y = mm(o.reshape(BATCH, nq), st.wo[l])                    # [B, hidden]
         if out is not None:
             out.copy_(y)
@@ -252,14 +273,17 @@ def cpu_baseline(seconds_budget: float = 20.0):
     lens = np.full(b, CTX)
     slots = bt[np.arange(b), (lens - 1) // PAGE].astype(np.int64) * PAGE + (lens - 1) % PAGE
     kcb, vcb = orc.from_f32(kc, True).ravel(), orc.from_f32(vc, True).ravel()   # flat storage bits
+    cos, sin = orc.rope_tables(D, CTX + PAGE, is_bf16=True)
     t0 = time.perf_counter()
     n = 0
     while True:  # one "layer" of the path for b sequences
         qkv = orc.round_to_io((x @ wqkv.T).astype(np.float32), True)
         nq, nkv = H * D, HK * D
-        q = np.ascontiguousarray(qkv[:, :nq]).reshape(b, 1, H, D)
-        orc.reshape_and_cache_flash(orc.from_f32(qkv, True).ravel()[nq:], orc.from_f32(qkv, True).ravel()[nq + nkv:],
-                                    kcb, vcb, slots, PAGE * nkv, b, HK, D, PAGE, qkv.shape[1], qkv.shape[1])
+        q3 = orc.round_to_io(orc.rope(qkv[:, :nq].reshape(b, H, D), lens - 1, cos, sin).astype(np.float32), True)
+        k3 = orc.round_to_io(orc.rope(qkv[:, nq:nq + nkv].reshape(b, HK, D), lens - 1, cos, sin).astype(np.float32), True)
+        q = q3.reshape(b, 1, H, D)
+        orc.reshape_and_cache_flash(orc.from_f32(k3, True).ravel(), orc.from_f32(qkv, True).ravel()[nq + nkv:],
+                                    kcb, vcb, slots, PAGE * nkv, b, HK, D, PAGE, nkv, qkv.shape[1])
         o, _ = orc.attention_paged_decode(q, orc.to_f32(kcb, True).reshape(kc.shape), orc.to_f32(vcb, True).reshape(vc.shape),
                                           bt, lens, D ** -0.5, True, precision="reference")
         x2 = orc.round_to_io((o.reshape(b, nq) @ wo.T).astype(np.float32), True)
@@ -519,8 +543,8 @@ def main():
             "data": "synthetic (seeded N(0,1) activations / KV caches, random-init weights, random block tables)",
             "config": {
                 "workload": f"BASELINE.json configs[1]: Llama-3.1-8B bf16 batch=32 ctx=4096 decode-only, block_size=16; "
-                            f"attention path of one decode step ({st.layers} layers x [fused qkv GEMM, reshape_and_cache_flash, "
-                            f"paged decode attention, o_proj GEMM]); RoPE/MLP/norms/lm_head not in SURVEY §8 scope and not timed",
+                            f"attention path of one decode step ({st.layers} layers x [fused qkv GEMM, RoPE + reshape_and_cache_flash, "
+                            f"paged decode attention, o_proj GEMM]); MLP/norms/lm_head not in SURVEY §8 scope and not timed",
                 "batch": BATCH, "ctx": CTX, "layers": st.layers, "heads": H, "kv_heads": HK, "head_dim": D,
                 "block_size": PAGE, "parallelism": f"tp{tp}",
                 "l2": "inputs larger than L2: 541 MB of KV per layer, 17.3 GB per step, distinct per layer",

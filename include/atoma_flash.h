@@ -120,6 +120,25 @@ void run_mha_stream(void *q_ptr, void *k_ptr, void *v_ptr, void *o_ptr, void *so
                     void *oaccum_ptr, atoma_stream_t stream);
 
 /*
+ * Fused rotary embedding + cache write (the reference's apply_rotary_embed x2 + transposes +
+ * reshape_and_cache_flash, models/src/llama.rs:218-251, 269-304 and flash_attention.rs:361, as one
+ * kernel).  q [T, num_heads, head_size] and k [T, num_kv_heads, head_size] (token strides q_stride /
+ * k_stride, elements) are rotated IN PLACE with the non-interleaved ("rotate half") convention of
+ * candle_nn::rotary_emb::rope: out[:d/2] = x1*cos - x2*sin, out[d/2:] = x1*sin + x2*cos, where
+ * cos/sin [max_pos, head_size/2] (row stride rot_stride, same dtype as q) are indexed by
+ * positions[t]; arithmetic in fp32, one rounding.  The rotated k and v [T, num_kv_heads, head_size]
+ * are then written to key_cache / value_cache at slot_mapping[t] exactly like
+ * reshape_and_cache_flash (slot < 0: token skipped; slot_mapping may be NULL: rotate only).
+ */
+void atoma_rope_reshape_and_cache(void *q, void *k, void *v, void *key_cache, void *value_cache,
+                                  const int64_t *positions, const void *cos, const void *sin,
+                                  const int64_t *slot_mapping, int64_t num_tokens, int64_t num_heads,
+                                  int64_t num_kv_heads, int64_t head_size, int64_t q_stride,
+                                  int64_t k_stride, int64_t v_stride, int64_t rot_stride,
+                                  int64_t block_stride, int64_t block_size, uint32_t dtype,
+                                  atoma_stream_t stream);
+
+/*
  * Batched block swap: for p < num_pairs copy block_bytes bytes from
  * src_base + src_blocks[p]*block_bytes to dst_base + dst_blocks[p]*block_bytes.
  * kind: 0 = device->device (one kernel launch, 16-byte vectors; src_blocks/dst_blocks are HOST

@@ -238,6 +238,33 @@ def swap_blocks(src: np.ndarray, dst: np.ndarray, block_mapping: dict, block_num
 
 
 # ------------------------------------------------------------------------------------------------
+# Rotary embedding (adjacent op of the attention path)
+# ------------------------------------------------------------------------------------------------
+def rope_tables(head_dim: int, max_pos: int, theta: float = 500000.0, is_bf16: bool = True):
+    """cos/sin [max_pos, head_dim/2] as the reference builds them (models/src/llama.rs:145-199,
+    default rope type): inv_freq_i = theta^(-2i/d) in f32, idx_theta = pos * inv_freq, tables cast
+    to the model dtype.  Returned as float32 values representable in that dtype."""
+    inv = (1.0 / theta ** (np.arange(0, head_dim, 2, dtype=np.float32) / np.float32(head_dim))).astype(np.float32)
+    ang = np.arange(max_pos, dtype=np.float32)[:, None] * inv[None, :]
+    return round_to_io(np.cos(ang).astype(np.float32), is_bf16), round_to_io(np.sin(ang).astype(np.float32), is_bf16)
+
+
+def rope(x: np.ndarray, positions: np.ndarray, cos: np.ndarray, sin: np.ndarray) -> np.ndarray:
+    """Non-interleaved rotary embedding of x [T, heads, d] (float, un-rounded result in float64):
+    models/src/llama.rs:218-251 selects cos/sin rows by position and calls
+    candle_nn::rotary_emb::rope (candle-nn 0.9.2-alpha.1, not vendored in /root/reference), whose
+    published contract is out[:d/2] = x1*cos - x2*sin, out[d/2:] = x1*sin + x2*cos with
+    x1 = x[..., :d/2], x2 = x[..., d/2:].  Parity for this op is unpinned in the reference (no test
+    asserts rotated values)."""
+    x = np.asarray(x, dtype=np.float64)
+    d = x.shape[-1]
+    c = np.asarray(cos, dtype=np.float64)[np.asarray(positions)][:, None, :]
+    s_ = np.asarray(sin, dtype=np.float64)[np.asarray(positions)][:, None, :]
+    x1, x2 = x[..., : d // 2], x[..., d // 2:]
+    return np.concatenate([x1 * c - x2 * s_, x1 * s_ + x2 * c], axis=-1)
+
+
+# ------------------------------------------------------------------------------------------------
 # Shape-level conveniences used by the tests
 # ------------------------------------------------------------------------------------------------
 def attention_dense(q: np.ndarray, k: np.ndarray, v: np.ndarray, scale: float, causal: bool,
