@@ -61,7 +61,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=L, help="debug only; the reported config needs 32")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--graph-tp", action="store_true", help="also capture the tensor-parallel step (NCCL inside the graph)")
+    ap.add_argument("--tp-comm", default="nccl", choices=["nccl", "torch"],
+                    help="N>1: 'nccl' = direct ncclAllReduce on the step's stream, whole step in one CUDA graph "
+                         "(atoma_infer_b200/nccl.py); 'torch' = torch.distributed.all_reduce launched eagerly between per-layer graphs")
     ap.add_argument("--gemm", default="auto", choices=["auto", "atoma", "cublas"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true", help="progress markers on stderr")
@@ -175,9 +177,11 @@ class State:
         self.out_host.copy_(self.out, non_blocking=True)
 
 
-def make_step(st: State, impl: str, gemm: str, dist):
+def make_step(st: State, impl: str, gemm: str, dist, comm=None):
     """Returns step() -> None that runs all layers on the current stream and leaves the result in
-    st.out."""
+    st.out.  With `comm` (a direct NCCL communicator) the all-reduce after o_proj is enqueued on the
+    same stream, in place on ping-pong buffers from comm.symmetric_empty (capturable); otherwise it
+    goes through torch.distributed."""
     torch = st.torch
     nq, nkv = st.h * D, st.hk * D
     d = st.devt
@@ -185,10 +189,10 @@ def make_step(st: State, impl: str, gemm: str, dist):
     if impl == "ours":
         from atoma_infer_b200 import ops
 
-        def mm(a, w):
+        def mm(a, w, out=None):
             if gemm == "atoma":
-                return ops.gemm_bf16_tn(a, w)
-            return torch.matmul(a, w.t())
+                return ops.gemm_bf16_tn(a, w, out)
+            return torch.matmul(a, w.t(), out=out)
 
         def attn(q, kc, vc, layer):
             return ops.flash_attn_kv_cache_full(q, kc, vc, None, st.scale, d["bt"], d["lens"], True)
@@ -203,8 +207,8 @@ def make_step(st: State, impl: str, gemm: str, dist):
         sms = torch.cuda.get_device_properties(st.dev).multi_processor_count
         stream0 = 0  # legacy default stream, like the reference (flash_api.cu:157)
 
-        def mm(a, w):
-            return torch.matmul(a, w.t())
+        def mm(a, w, out=None):
+            return torch.matmul(a, w.t(), out=out)
 
         def attn(q, kc, vc, layer):
             plan = ops.flash_attn_kv_cache_plan(q, kc, vc, st.scale, block_table=d["bt"], seqlens_k=d["lens"],
@@ -238,18 +242,18 @@ def make_step(st: State, impl: str, gemm: str, dist):
         kc, vc = st.kv[l][0], st.kv[l][1]
         q, k = rope_and_cache_write(q, k, v, kc, vc)
         o = attn(q.unsqueeze(1), kc, vc, l)                       # [B, 1, h, D]
-        y = mm(o.reshape(BATCH, nq), st.wo[l])                    # [B, hidden]
-        if out is not None:
-            out.copy_(y)
-            return out
-        return y
+        return mm(o.reshape(BATCH, nq), st.wo[l], out)            # [B, hidden]
 
     def step():
         x = d["x"]
         for l in range(st.layers):
-            x = layer(l, x)
-            if st.world > 1:
-                dist.all_reduce(x)                                    # multi_gpu.rs:141-179
+            if comm is not None:
+                x = layer(l, x, out=st.tp_bufs[l % 2])
+                comm.all_reduce_(x)                                   # multi_gpu.rs:141-179, on this stream
+            else:
+                x = layer(l, x)
+                if st.world > 1:
+                    dist.all_reduce(x)                                # multi_gpu.rs:141-179
         st.out.copy_(x)
 
     step.layer = layer
@@ -296,6 +300,27 @@ def cpu_baseline(seconds_budget: float = 20.0):
     return {"value": tok_s, "unit": "tokens/s", "cores": 1, "kind": "port",
             "sample": f"numpy oracle (oracle/attention_oracle.py), {n} layer pass(es) of the same path for {b} of "
                       f"the 32 sequences at ctx {CTX}; scaled to 32 layers"}
+
+
+def ncu_traffic(kernel_substr: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the newest
+    committed `ncu --set full` capture under profiles/ (taken with scripts/gpu_profile.sh on the same
+    config-2 inputs); None when no capture is present.  Evidence, not a timing."""
+    import csv
+    best = None
+    for f in sorted((ROOT / "profiles").glob("r*_ncu_full_raw.csv")):
+        try:
+            rows = list(csv.reader(open(f)))
+            h = rows[0]
+            kn, rd, wr = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            vals = [float(r[rd]) * unit[rows[1][rd]] + float(r[wr]) * unit[rows[1][wr]]
+                    for r in rows[2:] if kernel_substr in r[kn]]
+            if vals:
+                best = {"bytes": sum(vals) / len(vals), "file": f"profiles/{f.name}"}
+        except Exception:
+            continue
+    return best
 
 
 # ------------------------------------------------------------------------------------------------
@@ -353,7 +378,13 @@ def main():
     mark("init done, building state")
     st = State(torch, rank if args.impl == "ours" else 0, tp, args.layers, dev)
     mark("state built")
-    step = make_step(st, args.impl, gemm, dist)
+    comm = None
+    if dist is not None and args.tp_comm == "nccl":
+        from atoma_infer_b200 import nccl
+        comm = nccl.init_from_torch_distributed(dev)
+        st.tp_bufs = [comm.symmetric_empty((BATCH, HIDDEN), torch.bfloat16, dev) for _ in range(2)]
+        mark(f"direct NCCL communicator up (NCCL {nccl.version()}, {comm.symmetric_windows()} symmetric windows)")
+    step = make_step(st, args.impl, gemm, dist, comm)
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -367,8 +398,9 @@ def main():
     torch.cuda.synchronize()
     mark("first eager step done")
     launches_per_step = ops.launch_count() if args.impl == "ours" else 0
-    # NCCL collectives are launched eagerly: the tensor-parallel step is not graph-captured
-    use_graph = args.impl == "ours" and not args.no_graph and (world == 1 or args.graph_tp)
+    # torch.distributed's NCCL collectives are launched eagerly (not graph-captured); the direct
+    # communicator's are captured with the rest of the step
+    use_graph = args.impl == "ours" and not args.no_graph and (world == 1 or comm is not None)
     graph = None
     if use_graph:
         try:
@@ -548,7 +580,8 @@ def main():
                 "batch": BATCH, "ctx": CTX, "layers": st.layers, "heads": H, "kv_heads": HK, "head_dim": D,
                 "block_size": PAGE, "parallelism": f"tp{tp}",
                 "l2": "inputs larger than L2: 541 MB of KV per layer, 17.3 GB per step, distinct per layer",
-                "launch": ("cuda graph replay" if graph is not None else
+                "launch": ("cuda graph replay" + (" (NCCL all-reduces captured in the graph)" if comm is not None else "")
+                           if graph is not None else
                            "one cuda graph per layer + eager NCCL all-reduce" if layer_graphs is not None else
                            "eager, one host thread") +
                           (", programmatic dependent launch" if args.impl == "ours" and not args.no_pdl else ""),
@@ -566,6 +599,11 @@ def main():
                          "us_per_launch": us_kernel, "algorithmic_bytes_per_launch": alg_bytes,
                          "frac_of_8TBps": achieved / 8000.0, "traffic": None},
         }
+        if args.impl == "ours" and tp == 1 and st.layers == L:
+            t = ncu_traffic("decode_paged_kernel")
+            if t:
+                line["roofline"]["traffic"] = t["bytes"]
+                line["roofline"]["traffic_source"] = t["file"] + " (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, same inputs)"
         if args.impl == "reference":
             line["impl"] = "reference"
             line["value"] = line["e2e"]["value"]   # the reference's number is host-timed by definition
@@ -582,6 +620,10 @@ def main():
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
+        torch.cuda.synchronize()
+        if comm is not None:
+            run = graph = None   # the graph holds the captured collectives: drop it before the communicator
+            comm.destroy()
         dist.destroy_process_group()
 
 
