@@ -151,6 +151,15 @@ __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *m
         "r"(c3), "l"(policy)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(void *smem_dst, const CUtensorMap *map, uint64_t *bar,
+                                            int c0, int c1, int c2, int c3, int c4, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3), "r"(c4), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar,
                                             int c0, int c1, uint64_t policy) {
     asm volatile(

@@ -13,12 +13,17 @@
 //    persistent grid of min(#SM, units) CTAs takes equal contiguous slices of that list
 //    (stream-K), so the 1.73-wave imbalance of one-CTA-per-(sequence, head) never appears and no
 //    caller-chosen num_splits is needed.
-//  * One producer warp streams K and V with TMA (cp.async.bulk.tensor, 128-byte swizzle) straight
-//    out of the reference's [num_blocks, block_size, num_kv_heads, head_size] cache layout: a box is
-//    [64 d][TB tokens][HKT heads] of one physical page, i.e. for Llama-3.1-8B two boxes cover one
-//    whole contiguous 32 KiB K page (all 8 kv heads).  Page ids are prefetched 32 at a time from
-//    the block table with one coalesced load and never past ceil(len / page) (the reference reads
-//    up to 7 entries past it).
+//  * A producer warpgroup streams K and V with TMA (cp.async.bulk.tensor, 128-byte swizzle) straight
+//    out of the reference's [num_blocks, block_size, num_kv_heads, head_size] cache layout.  For
+//    D = 128 the cache is described as a 5-D tensor {64 d, token, 2 halves of d, kv head, page}, so
+//    ONE op moves [HKT heads][2 halves][TB tokens][64 d] of a physical page — for Llama-3.1-8B one
+//    whole contiguous 32 KiB K page (all 8 kv heads).  Measured (scripts/tma_probe.cu): an SM
+//    sustains only ~5 tensor ops/us from one issuing warp (~10 from four), so the op size decides
+//    the bandwidth: 16-32 KiB ops reach the HBM limit from one warp, the 4 KiB ops of a
+//    tensor-parallel shard with one kv head need all four producer warps.  The ops of a stage are
+//    dealt round-robin to the four warps.  Page ids are prefetched 32 at a time from the block
+//    table with one coalesced load and never past ceil(len / page) (the reference reads up to 7
+//    entries past it).
 //  * Eight consumer warps each own one (kv head, 16-token) slice of a stage and run the GQA group
 //    of that kv head as the M dimension of mma.sync m16n8k16 (all H/Hkv query heads share one pass
 //    over K/V; the reference re-streams K/V once per query head).
@@ -36,7 +41,8 @@ namespace {
 
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kDecodeThreads = kConsumerThreads + 128;  // + the producer warpgroup (one warp issues TMA)
+constexpr int kProducerWarps = 4;
+constexpr int kDecodeThreads = kConsumerThreads + 32 * kProducerWarps;  // + the producer warpgroup
 constexpr int kProducerRegs = 56;    // setmaxnreg: the producer warpgroup hands its registers ...
 constexpr int kConsumerRegs = 216;   // ... to the two consumer warpgroups (168 + 112 * 128 / 256)
 constexpr int kStageRows = 128;                        // (token, head) rows per stage
@@ -207,8 +213,8 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
 
     if (tid == 0) {
         for (int i = 0; i < C::kStages; ++i) {
-            mbar_init(&full_k[i], 1);
-            mbar_init(&full_v[i], 1);
+            mbar_init(&full_k[i], kProducerWarps);
+            mbar_init(&full_v[i], kProducerWarps);
             mbar_init(&empty[i], kConsumerWarps);
         }
         fence_mbar_init();
@@ -272,9 +278,11 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
     if (cta >= ncta) return;
     const long long u_begin = cta_start(units, cta, ncta), u_end = cta_start(units, cta + 1, ncta);
 
-    const int box_rows = a.hkt * a.tb;            // 128-byte lines per box
+    // One box = [hkt heads][kHalves][tb tokens] 128-byte lines (one tensor op).
+    const int box_rows = a.hkt * C::kHalves * a.tb;
     const uint32_t box_bytes = box_rows * 128u;
-    const int boxes_per_half = a.tok / a.tb;
+    const int boxes_per_stage = a.tok / a.tb;
+    const uint32_t half_stride = a.tb * 128u;     // bytes between the two 64-wide halves of a row
 
     int stage = 0;
     uint32_t phase = 0;
@@ -282,7 +290,7 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
     if (warp >= kConsumerWarps) {
         // =========================== producer warpgroup ===========================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
-        if (warp != kConsumerWarps) return;  // warps 9..11 only lend their registers
+        const int pw = warp - kConsumerWarps;  // ops o = 0..2*nbx-1 of a stage (K boxes, then V boxes): warp o % 4
         long long u = u_begin;
         int b = 0;
         while (u < u_end) {
@@ -300,10 +308,9 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
                 __syncwarp();
                 const int tok0 = s * a.tok;
                 int nbx = (len - tok0 + a.tb - 1) / a.tb;
-                nbx = min(nbx, boxes_per_half);
+                nbx = min(nbx, boxes_per_stage);
                 unsigned char *ks = tiles + stage * C::kStageBytes;
                 unsigned char *vs = ks + C::kTileBytes;
-                if (lane == 0) mbar_arrive_expect_tx(&full_k[stage], nbx * C::kHalves * box_bytes);
                 int phys[8];
 #pragma unroll
                 for (int bx = 0; bx < 8; ++bx) {
@@ -318,27 +325,37 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
                     }
                 }
                 if (lane == 0) {
+                    // this warp's share: K box bx when bx % 4 == pw, V box bx when (nbx + bx) % 4 == pw
+                    int nk = 0, nv = 0;
 #pragma unroll
                     for (int bx = 0; bx < 8; ++bx) {
-                        if (bx < nbx) {
-                            const int t_in_page = (tok0 + bx * a.tb) % p.page;
+                        nk += (bx < nbx && (bx & 3) == pw) ? 1 : 0;
+                        nv += (bx < nbx && ((nbx + bx) & 3) == pw) ? 1 : 0;
+                    }
+                    mbar_arrive_expect_tx(&full_k[stage], nk * box_bytes);
 #pragma unroll
-                            for (int hf = 0; hf < C::kHalves; ++hf)
-                                tma_load_4d(ks + hf * C::kHalfBytes + bx * box_bytes, &map_k,
-                                            &full_k[stage], hf * 64, t_in_page, hg * a.hkt, phys[bx],
-                                            kL2EvictFirst);
+                    for (int bx = 0; bx < 8; ++bx) {
+                        if (bx < nbx && (bx & 3) == pw) {
+                            const int t_in_page = (tok0 + bx * a.tb) % p.page;
+                            if (C::kHalves == 2)
+                                tma_load_5d(ks + bx * box_bytes, &map_k, &full_k[stage], 0, t_in_page, 0,
+                                            hg * a.hkt, phys[bx], kL2EvictFirst);
+                            else
+                                tma_load_4d(ks + bx * box_bytes, &map_k, &full_k[stage], 0, t_in_page,
+                                            hg * a.hkt, phys[bx], kL2EvictFirst);
                         }
                     }
-                    mbar_arrive_expect_tx(&full_v[stage], nbx * C::kHalves * box_bytes);
+                    mbar_arrive_expect_tx(&full_v[stage], nv * box_bytes);
 #pragma unroll
                     for (int bx = 0; bx < 8; ++bx) {
-                        if (bx < nbx) {
+                        if (bx < nbx && ((nbx + bx) & 3) == pw) {
                             const int t_in_page = (tok0 + bx * a.tb) % p.page;
-#pragma unroll
-                            for (int hf = 0; hf < C::kHalves; ++hf)
-                                tma_load_4d(vs + hf * C::kHalfBytes + bx * box_bytes, &map_v,
-                                            &full_v[stage], hf * 64, t_in_page, hg * a.hkt, phys[bx],
-                                            kL2EvictFirst);
+                            if (C::kHalves == 2)
+                                tma_load_5d(vs + bx * box_bytes, &map_v, &full_v[stage], 0, t_in_page, 0,
+                                            hg * a.hkt, phys[bx], kL2EvictFirst);
+                            else
+                                tma_load_4d(vs + bx * box_bytes, &map_v, &full_v[stage], 0, t_in_page,
+                                            hg * a.hkt, phys[bx], kL2EvictFirst);
                         }
                     }
                 }
@@ -358,7 +375,8 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
     const int hh = warp % a.hkt;          // kv head within the group
     const int ts = warp / a.hkt;          // 16-token slice within the stage
     const int bx_w = (ts * 16) / a.tb;    // box holding this warp's tokens
-    const int row_base = bx_w * box_rows + hh * a.tb + (ts * 16) % a.tb;  // 128-byte line index
+    // 128-byte line index of this warp's first token, first half: box layout [head][half][token]
+    const int row_base = bx_w * box_rows + hh * C::kHalves * a.tb + (ts * 16) % a.tb;
     const int G = a.g;
 
     long long u = u_begin;
@@ -410,7 +428,7 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
                     for (int kk = 0; kk < D / 16; ++kk) {
                         const int c = kk * 2 + ((lane >> 3) & 1);  // 16-byte chunk over D
                         uint32_t bf[4];
-                        ldmatrix_x4(bf, line + (c >> 3) * C::kHalfBytes + (((c & 7) ^ (lane & 7)) << 4));
+                        ldmatrix_x4(bf, line + (c >> 3) * half_stride + (((c & 7) ^ (lane & 7)) << 4));
                         Mma16816<T>::run(sc[0], qf[kk], bf[0], bf[1]);
                         Mma16816<T>::run(sc[1], qf[kk], bf[2], bf[3]);
                     }
@@ -474,7 +492,7 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
                         const int i = idx / (D / 8), c = idx % (D / 8);
                         if (i >= nvalid)
                             *reinterpret_cast<uint4 *>(tiles + (vs - smem_u32(tiles)) +
-                                                       (c >> 3) * C::kHalfBytes + (row_base + i) * 128 +
+                                                       (c >> 3) * half_stride + (row_base + i) * 128 +
                                                        (((c & 7) ^ (i & 7)) << 4)) = make_uint4(0, 0, 0, 0);
                     }
                     __syncwarp();
@@ -487,7 +505,7 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
                     for (int dj2 = 0; dj2 < D / 16; ++dj2) {
                         const int c = dj2 * 2 + (lane >> 4);
                         uint32_t vf[4];
-                        ldmatrix_x4_trans(vf, line + (c >> 3) * C::kHalfBytes + (((c & 7) ^ (lane & 7)) << 4));
+                        ldmatrix_x4_trans(vf, line + (c >> 3) * half_stride + (((c & 7) ^ (lane & 7)) << 4));
                         Mma16816<T>::run(o_acc[2 * dj2], pa, vf[0], vf[1]);
                         Mma16816<T>::run(o_acc[2 * dj2 + 1], pa, vf[2], vf[3]);
                     }
@@ -660,18 +678,33 @@ bool make_kv_map(CUtensorMap *out, const void *ptr, int64_t rs, int64_t hs, int6
         if (e.key == key) { *out = e.map; return true; }
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) return false;
-    // dims, fastest first: d, token-in-page, kv head, physical page.  The page count is not part of
-    // the run_mha ABI; any id the block table can hold must be addressable.
-    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(page),
-                                static_cast<cuuint64_t>(hk), static_cast<cuuint64_t>(1) << 22};
-    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(rs) * 2, static_cast<cuuint64_t>(hs) * 2,
-                                   static_cast<cuuint64_t>(bs) * 2};
-    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(tb), static_cast<cuuint32_t>(hkt), 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
-                     const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // dims, fastest first.  The page count is not part of the run_mha ABI; any id the block table can
+    // hold must be addressable.
+    //   D = 64 : {d, token-in-page, kv head, physical page}, box {64, tb, hkt, 1}
+    //   D = 128: {64 d, token-in-page, half of d (stride 128 B), kv head, physical page},
+    //            box {64, tb, 2, hkt, 1}: both 128-byte halves of every row in one op, landing as
+    //            [head][half][token] lines (token & 7 stays the swizzle phase of a line).
+    const CUtensorMapDataType dt = is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUresult r;
+    if (d == 128) {
+        const cuuint64_t dims[5] = {64, static_cast<cuuint64_t>(page), 2, static_cast<cuuint64_t>(hk),
+                                    static_cast<cuuint64_t>(1) << 22};
+        const cuuint64_t strides[4] = {static_cast<cuuint64_t>(rs) * 2, 128, static_cast<cuuint64_t>(hs) * 2,
+                                       static_cast<cuuint64_t>(bs) * 2};
+        const cuuint32_t box[5] = {64, static_cast<cuuint32_t>(tb), 2, static_cast<cuuint32_t>(hkt), 1};
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        r = enc(out, dt, 5, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(page),
+                                    static_cast<cuuint64_t>(hk), static_cast<cuuint64_t>(1) << 22};
+        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(rs) * 2, static_cast<cuuint64_t>(hs) * 2,
+                                       static_cast<cuuint64_t>(bs) * 2};
+        const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(tb), static_cast<cuuint32_t>(hkt), 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        r = enc(out, dt, 4, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) {
         set_status(kErrDriver, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
         return false;

@@ -380,6 +380,7 @@ bool make_operand_map(CUtensorMap *out, const void *ptr, int64_t rows, int64_t c
 }
 
 void *g_gemm_trace = nullptr;
+int g_gemm_stage_limit = 0;  // diagnostics (atoma_debug_gemm_stages): 0 = as many as fit
 
 bool launch_stream_gemm(const void *x, const void *w, void *y, int T, int64_t N, int64_t K, int64_t ldx,
                         int64_t ldw, int64_t ldy, bool is_bf16, cudaStream_t stream) {
@@ -396,6 +397,7 @@ bool launch_stream_gemm(const void *x, const void *w, void *y, int T, int64_t N,
     a.tmem_cols = cols;
     const int stage_bytes = kWBytes + a.t_pad * 128;
     a.stages = std::min(kMaxStages, (200 * 1024) / stage_bytes);
+    if (g_gemm_stage_limit > 0) a.stages = std::max(2, std::min(a.stages, g_gemm_stage_limit));
     const size_t smem = static_cast<size_t>(a.stages) * stage_bytes + 1024;
     const int64_t units = static_cast<int64_t>(a.tiles) * a.kb_per_tile;
     const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min(di.sm_count, kGemmMaxCtas), units)));
@@ -436,6 +438,7 @@ bool launch_stream_gemm(const void *x, const void *w, void *y, int T, int64_t N,
 }  // namespace
 
 void set_gemm_trace(void *device_buf) { g_gemm_trace = device_buf; }
+void set_gemm_stage_limit(int stages) { g_gemm_stage_limit = stages; }
 
 bool launch_gemm_bf16_tn(const void *x, const void *w, void *y, int64_t T, int64_t N, int64_t K,
                          int64_t ldx, int64_t ldw, int64_t ldy, cudaStream_t stream) {

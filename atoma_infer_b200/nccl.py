@@ -11,8 +11,11 @@ per-layer graphs.
 
 The collective itself stays NCCL (north star: "keeps the repo's existing NCCL allreduce ... reported
 but not re-implemented").  Buffers may be allocated with `ncclMemAlloc` and registered as symmetric
-windows (`ncclCommWindowRegister`, NCCL >= 2.27) so NCCL can pick its low-latency symmetric kernels
-over NVLink; registration is optional and failures fall back to plain buffers.
+windows (`ncclCommWindowRegister`, NCCL >= 2.27) so NCCL can pick its symmetric kernels over NVLink.
+Registration is OFF by default (ATOMA_NCCL_SYMMETRIC=1 switches it on): measured on 2 x B200 with NCCL
+2.28.9 (scripts/nccl_diag.py) the symmetric kernel is slower for this 256 KiB payload (25.0 vs 21.6 us)
+and its bf16 sum is not the correctly rounded a + b (19 % of elements off by one ulp), where the
+default ring/tree path returns RN(a + b) exactly.
 
 No CPU fallback: every call raises `NcclError` when the library reports an error.
 """
@@ -146,8 +149,9 @@ class Comm:
         return t
 
     def symmetric_empty(self, shape, dtype, device):
-        """A tensor over `ncclMemAlloc` memory registered as a symmetric window when the library
-        supports it (collective call: every rank must make it, with the same size)."""
+        """A tensor over `ncclMemAlloc` memory, registered as a symmetric window when
+        ATOMA_NCCL_SYMMETRIC=1 and the library supports it (collective call: every rank must make
+        it, with the same size)."""
         import torch
         item = torch.empty((), dtype=dtype).element_size()
         n = 1
@@ -157,7 +161,7 @@ class Comm:
         ptr = C.c_void_p()
         _check(lib().ncclMemAlloc(C.byref(ptr), nbytes), "ncclMemAlloc")
         win = None
-        if hasattr(lib(), "ncclCommWindowRegister") and os.environ.get("ATOMA_NCCL_SYMMETRIC", "1") != "0":
+        if hasattr(lib(), "ncclCommWindowRegister") and os.environ.get("ATOMA_NCCL_SYMMETRIC", "0") == "1":
             w = C.c_void_p()
             rc = lib().ncclCommWindowRegister(self.handle, ptr, nbytes, C.byref(w), NCCL_WIN_COLL_SYMMETRIC)
             win = w.value if rc == 0 else None

@@ -182,6 +182,8 @@ int atoma_get_launch_mode(void);
 void atoma_debug_decode_trace(void *device_buf);
 /* Same for the projection GEMM: {start, first operand tile landed, last accumulator complete, end}. */
 void atoma_debug_gemm_trace(void *device_buf);
+/* Diagnostics: cap the GEMM's shared-memory ring at `stages` stages (0 = as many as fit). */
+void atoma_debug_gemm_stages(int stages);
 
 /* 0 = last call on this thread succeeded; otherwise a negative atoma code or a cudaError_t. */
 int atoma_last_status(void);

@@ -1,6 +1,7 @@
 """Kernel-level timing of the paged decode attention at BASELINE.json config 2 (per layer):
 ours vs the reference kernels (oracle/_ref), CUDA events, L2 defeated by rotating caches."""
 import json
+import os
 import sys
 import time
 from pathlib import Path
@@ -16,7 +17,8 @@ from atoma_infer_b200 import ops  # noqa: E402
 
 def main():
     dev = "cuda:0"
-    B, H, HK, D, page, MB = 32, 32, 8, 128, 16, 256
+    HK = int(os.environ.get("ATOMA_MB_HK", "8"))   # kv heads on this rank (8 / tensor-parallel degree)
+    B, H, D, page, MB = 32, 4 * HK, 128, 16, 256
     ctx = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
     NB = B * MB + 64
     nrot = 4
@@ -29,7 +31,7 @@ def main():
     scale = 1.0 / np.sqrt(D)
     bytes_alg = 2 * B * ctx * HK * D * 2 + 2 * B * H * D * 2 + B * MB * 4
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    res = {"ctx": ctx, "bytes": bytes_alg, "sms": sms}
+    res = {"ctx": ctx, "kv_heads": HK, "bytes": bytes_alg, "sms": sms}
 
     def time_it(fn, iters=40, warm=8):
         for i in range(warm):
@@ -61,6 +63,8 @@ def main():
     res["ours_GBps"] = bytes_alg / med / 1e9
     print(json.dumps(res), flush=True)
 
+    if "--only-ours" in sys.argv:
+        return
     # read-only / copy bandwidth probes on the same box (context for the roofline fraction)
     big = torch.empty(1 << 31, dtype=torch.uint8, device=dev)
     big.zero_()
@@ -103,7 +107,7 @@ def main():
         res["max_abs_diff_vs_ref"] = float((out.float() - out2.float()).abs().max())
     print(json.dumps(res), flush=True)
     Path(ROOT / "gpurun_out").mkdir(exist_ok=True)
-    (ROOT / "gpurun_out" / f"microbench_decode_{ctx}.json").write_text(json.dumps(res, indent=1))
+    (ROOT / "gpurun_out" / f"microbench_decode_{ctx}_hk{HK}.json").write_text(json.dumps(res, indent=1))
 
 
 if __name__ == "__main__":

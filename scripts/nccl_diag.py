@@ -1,0 +1,59 @@
+"""2-GPU diagnostic: numerics and latency of the direct NCCL all-reduce (eager, graph, symmetric on/off)."""
+import os
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from atoma_infer_b200 import nccl  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    torch.cuda.set_device(dev)
+    dist.init_process_group("gloo")
+    comm = nccl.init_from_torch_distributed(dev)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    parts = [torch.randn((32, 4096), generator=g).to(torch.bfloat16) for _ in range(world)]
+    exact = sum(p.double() for p in parts)
+    want = exact.float().to(torch.bfloat16).float()
+    for label, buf in (("symmetric", comm.symmetric_empty((32, 4096), torch.bfloat16, dev)),
+                       ("plain", torch.empty((32, 4096), dtype=torch.bfloat16, device=dev))):
+        buf.copy_(parts[rank].to(dev))
+        comm.all_reduce_(buf)
+        torch.cuda.synchronize()
+        got = buf.float().cpu()
+        nbad = int((got != want).sum())
+        err = (got.double() - exact).abs()
+        werr = (want.double() - exact).abs()
+        # timing: graph of 64 all-reduces
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            comm.all_reduce_(buf)
+        s.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s):
+            for _ in range(64):
+                comm.all_reduce_(buf)
+        gr.replay(); torch.cuda.synchronize()
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            gr.replay()
+        b.record(); torch.cuda.synchronize()
+        us = a.elapsed_time(b) * 1e3 / (5 * 64)
+        print(f"[r{rank}] {label}: windows={comm.symmetric_windows()} mismatches vs RN(sum)={nbad}/{got.numel()} "
+              f"max|got-exact|={err.max():.4g} max|RN-exact|={werr.max():.4g} got_is_rounder={bool((err <= werr + 1e-12).all())} "
+              f"all-reduce 256KiB in graph: {us:.2f} us", flush=True)
+        del gr
+    comm.destroy()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,4 +1,5 @@
 """Per-CTA timeline of the paged decode kernel at config 2 (diagnostics; uses atoma_debug_decode_trace)."""
+import os
 import sys
 from pathlib import Path
 
@@ -12,7 +13,8 @@ from atoma_infer_b200 import _lib, ops  # noqa: E402
 
 def main():
     dev = "cuda:0"
-    B, H, HK, D, page, MB = 32, 32, 8, 128, 16, 256
+    HK = int(os.environ.get("ATOMA_MB_HK", "8"))   # kv heads on this rank (8 / tensor-parallel degree)
+    B, H, D, page, MB = 32, 4 * HK, 128, 16, 256
     NB = B * MB + 64
     g = torch.Generator(device=dev).manual_seed(0)
     caches = [torch.randn((2, NB, page, HK, D), generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)

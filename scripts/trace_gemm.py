@@ -14,7 +14,7 @@ def main():
     dev = "cuda:0"
     L = _lib.lib()
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    for (T, N, K) in [(32, 6144, 4096), (1, 3072, 2048)]:
+    for (T, N, K) in [(32, 6144, 4096), (32, 4096, 4096), (1, 3072, 2048)]:
         ws = [torch.randn((N, K), device=dev).to(torch.bfloat16) for _ in range(4)]
         x = torch.randn((T, K), device=dev).to(torch.bfloat16)
         for i in range(8):
