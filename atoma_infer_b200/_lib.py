@@ -132,6 +132,16 @@ SIGNATURES = {
     "swap_blocks_batched": (None, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                    C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
     "atoma_gemm_bf16_tn": (None, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int64] * 6 + [C.c_void_p]),
+    "atoma_p2p_region_bytes": (C.c_int64, [C.c_int64]),
+    "atoma_p2p_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
+    "atoma_p2p_free": (C.c_int, [C.c_void_p]),
+    "atoma_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "atoma_p2p_import": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "atoma_p2p_close": (C.c_int, [C.c_void_p]),
+    "atoma_p2p_slot": (C.c_void_p, [C.c_void_p, C.c_int64, C.c_int]),
+    "atoma_p2p_error": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "atoma_allreduce_sum_p2p": (None, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p,
+                                       C.c_int64, C.c_uint32, C.c_void_p]),
     "atoma_debug_decode_trace": (None, [C.c_void_p]),
     "atoma_debug_gemm_trace": (None, [C.c_void_p]),
     "atoma_debug_gemm_stages": (None, [C.c_int]),

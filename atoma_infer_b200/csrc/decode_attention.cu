@@ -59,6 +59,10 @@ struct Cfg {
     static constexpr int kTileBytes = kHalves * kHalfBytes;  // K (or V) bytes per stage
     static constexpr int kStageBytes = 2 * kTileBytes;
     static constexpr int kStages = (192 * 1024) / kStageBytes;  // 3 (D=128) / 6 (D=64)
+    // In-CTA merge of the token-slice warps of one kv head (tensor-parallel shards, hkt < 8): up to four
+    // writers per round, each G <= 8 rows of fp32 O in register order + (max, sum) per row.
+    static constexpr int kTreeOBytes = 4 * (D / 8) * 32 * 8;
+    static constexpr int kTreeBytes = kTreeOBytes + 4 * 8 * 8;
 };
 
 struct DecodeArgs {
@@ -531,7 +535,42 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
             l_run[rr] += __shfl_xor_sync(0xffffffffu, l_run[rr], 1);
             l_run[rr] += __shfl_xor_sync(0xffffffffu, l_run[rr], 2);
         }
-        {
+        // Tensor-parallel shards put several token-slice warps on one kv head (hkt < 8).  Merge them
+        // inside the CTA first (binary tree through shared memory, fixed order), so that one partial
+        // per (CTA, kv head) is published and every head is reduced by one warp, exactly like hkt = 8.
+        const bool tree = a.hkt < kConsumerWarps && G <= 8;
+        if (tree) {
+            float2 *sm_o = reinterpret_cast<float2 *>(tiles + C::kStages * C::kStageBytes);
+            float2 *sm_ml = reinterpret_cast<float2 *>(tiles + C::kStages * C::kStageBytes + C::kTreeOBytes);
+            const int wpk = kConsumerWarps / a.hkt;
+            for (int step = 1; step < wpk; step <<= 1) {
+                const int sl = (ts / (2 * step)) * a.hkt + hh;  // < 4
+                if ((ts % (2 * step)) == step) {
+#pragma unroll
+                    for (int i = 0; i < D / 8; ++i)
+                        sm_o[(sl * (D / 8) + i) * 32 + lane] = make_float2(o_acc[i][0], o_acc[i][1]);
+                    if (t4 == 0) sm_ml[sl * 8 + g] = make_float2(m_run[0], l_run[0]);
+                }
+                named_bar_sync(1, kConsumerThreads);
+                if ((ts % (2 * step)) == 0) {
+                    const float2 mlb = sm_ml[sl * 8 + g];
+                    const float m_new = fmaxf(m_run[0], mlb.x);
+                    if (m_new != -INFINITY) {
+                        const float ca = fast_exp2(m_run[0] - m_new), cb = fast_exp2(mlb.x - m_new);
+#pragma unroll
+                        for (int i = 0; i < D / 8; ++i) {
+                            const float2 ob = sm_o[(sl * (D / 8) + i) * 32 + lane];
+                            o_acc[i][0] = o_acc[i][0] * ca + ob.x * cb;
+                            o_acc[i][1] = o_acc[i][1] * ca + ob.y * cb;
+                        }
+                        l_run[0] = l_run[0] * ca + mlb.y * cb;
+                        m_run[0] = m_new;
+                    }
+                }
+                named_bar_sync(1, kConsumerThreads);
+            }
+        }
+        if (!tree || ts == 0) {
             const int64_t part = (static_cast<int64_t>(cta) * 2 + slot) * kConsumerWarps + warp;
             float *po = a.ws_o + part * (kPartRows * D);
             float *pml = a.ws_ml + part * (kPartRows * 2);
@@ -552,10 +591,14 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
             }
         }
         const int fc = cta_of_unit(units, ub, ncta), lc = cta_of_unit(units, ue - 1, ncta);
-        if (a.hkt == kConsumerWarps) {
-            // One warp per kv head (Hkv a multiple of 8): every head is published and reduced on its
-            // own — no CTA-wide barrier, and the 8 reductions of a sequence land on whichever warps
-            // arrive last, usually on different SMs.
+        if (a.hkt == kConsumerWarps || tree) {
+            // One partial per kv head (Hkv a multiple of 8, or after the in-CTA merge): every head is
+            // published and reduced on its own — no CTA-wide barrier, and the reductions of a
+            // sequence land on whichever warps arrive last, usually on different SMs.
+            if (tree && ts != 0) {
+                u += n;
+                continue;
+            }
             __threadfence();
             __syncwarp();
             if (a.trace && tid == 0) a.trace[blockIdx.x * 8 + 4] = global_timer_ns();
@@ -719,7 +762,7 @@ void *g_decode_trace = nullptr;
 template <typename T, int D>
 bool launch_decode(const CUtensorMap &mk, const CUtensorMap &mv, const DecodeArgs &a,
                    cudaStream_t stream) {
-    constexpr size_t smem = Cfg<D>::kStages * Cfg<D>::kStageBytes + 1024;
+    constexpr size_t smem = Cfg<D>::kStages * Cfg<D>::kStageBytes + 1024 + Cfg<D>::kTreeBytes;
     static thread_local int attr_dev = -1;
     const DeviceInfo &di = current_device_info();
     if (attr_dev != di.ordinal) {

@@ -61,10 +61,15 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=L, help="debug only; the reported config needs 32")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--tp-comm", default="nccl", choices=["nccl", "torch"],
-                    help="N>1: 'nccl' = direct ncclAllReduce on the step's stream, whole step in one CUDA graph "
-                         "(atoma_infer_b200/nccl.py); 'torch' = torch.distributed.all_reduce launched eagerly between per-layer graphs")
+    ap.add_argument("--tp-comm", default="p2p", choices=["p2p", "nccl", "torch"],
+                    help="N>1, the all-reduce after o_proj: 'p2p' = this library's one-shot kernel over NVLink peer memory "
+                         "(csrc/allreduce_p2p.cu; falls back to 'nccl' if peer mapping fails); 'nccl' = direct ncclAllReduce on "
+                         "the step's stream (atoma_infer_b200/nccl.py); both are captured with the step in one CUDA graph; "
+                         "'torch' = torch.distributed.all_reduce launched eagerly between per-layer graphs")
     ap.add_argument("--gemm", default="auto", choices=["auto", "atoma", "cublas"])
+    ap.add_argument("--emulate-tp", type=int, default=0,
+                    help="diagnostics, one GPU: run ONE rank's shard of a tensor-parallel degree-N step (no all-reduce); "
+                         "the JSON line is marked and is not a bench value")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true", help="progress markers on stderr")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch between our kernels")
@@ -177,11 +182,12 @@ class State:
         self.out_host.copy_(self.out, non_blocking=True)
 
 
-def make_step(st: State, impl: str, gemm: str, dist, comm=None):
+def make_step(st: State, impl: str, gemm: str, dist, comm=None, p2p=None):
     """Returns step() -> None that runs all layers on the current stream and leaves the result in
-    st.out.  With `comm` (a direct NCCL communicator) the all-reduce after o_proj is enqueued on the
-    same stream, in place on ping-pong buffers from comm.symmetric_empty (capturable); otherwise it
-    goes through torch.distributed."""
+    st.out.  The all-reduce after o_proj (multi_gpu.rs:141-179) is, in this order of preference:
+    `p2p` — o_proj writes into the rank's peer-mapped slot and atoma_allreduce_sum_p2p sums the slots
+    of all ranks into a local buffer; `comm` (direct NCCL communicator) — ncclAllReduce in place on
+    ping-pong buffers; both on the step's stream (capturable); else torch.distributed."""
     torch = st.torch
     nq, nkv = st.h * D, st.hk * D
     d = st.devt
@@ -247,7 +253,10 @@ def make_step(st: State, impl: str, gemm: str, dist, comm=None):
     def step():
         x = d["x"]
         for l in range(st.layers):
-            if comm is not None:
+            if p2p is not None:
+                layer(l, x, out=st.tp_slots[l % 2])
+                x = p2p.all_reduce(l % 2, st.tp_out[l % 2])
+            elif comm is not None:
                 x = layer(l, x, out=st.tp_bufs[l % 2])
                 comm.all_reduce_(x)                                   # multi_gpu.rs:141-179, on this stream
             else:
@@ -333,6 +342,11 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if args.impl == "reference" and rank != 0:
         return  # rank 0 alone runs the reference arm
+    # The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner when
+    # NCCL_DEBUG is set in the environment): keep the real stdout aside and point fd 1 at stderr.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     def mark(msg):
         if args.verbose:
@@ -376,15 +390,41 @@ def main():
         # weights are immutable during a decode step: the GEMM may stream them ahead of its dependency
         ops.set_launch_mode(pdl=not args.no_pdl, const_weights=not args.no_pdl)
     mark("init done, building state")
+    if args.emulate_tp:
+        if world != 1 or args.impl != "ours":
+            raise SystemExit("--emulate-tp is a single-process diagnostic of our arm")
+        tp = args.emulate_tp
     st = State(torch, rank if args.impl == "ours" else 0, tp, args.layers, dev)
+    if args.emulate_tp:
+        st.world = 1   # no collective in the step
     mark("state built")
-    comm = None
-    if dist is not None and args.tp_comm == "nccl":
+    comm = p2p = None
+    tp_comm = args.tp_comm
+    if dist is not None and tp_comm == "p2p":
+        from atoma_infer_b200.p2p import P2PComm
+        ok = torch.ones(1, device=dev)
+        try:
+            if args.layers % 2:
+                raise RuntimeError("slots alternate per layer: the layer count must be even")
+            p2p = P2PComm.from_torch_distributed(dev, BATCH * HIDDEN * 2)
+        except Exception as e:
+            print(f"[bench r{rank}] peer-to-peer all-reduce unavailable ({e}); using NCCL", file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks take the same path
+        if ok.item() == 0:
+            if p2p is not None:
+                p2p.destroy()
+            p2p, tp_comm = None, "nccl"
+        else:
+            st.tp_slots = [p2p.slot(i, (BATCH, HIDDEN), torch.bfloat16) for i in range(2)]
+            st.tp_out = [torch.empty((BATCH, HIDDEN), device=dev, dtype=torch.bfloat16) for _ in range(2)]
+            mark("peer-to-peer all-reduce regions mapped")
+    if dist is not None and tp_comm == "nccl":
         from atoma_infer_b200 import nccl
         comm = nccl.init_from_torch_distributed(dev)
         st.tp_bufs = [comm.symmetric_empty((BATCH, HIDDEN), torch.bfloat16, dev) for _ in range(2)]
         mark(f"direct NCCL communicator up (NCCL {nccl.version()}, {comm.symmetric_windows()} symmetric windows)")
-    step = make_step(st, args.impl, gemm, dist, comm)
+    step = make_step(st, args.impl, gemm, dist, comm, p2p)
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -400,7 +440,7 @@ def main():
     launches_per_step = ops.launch_count() if args.impl == "ours" else 0
     # torch.distributed's NCCL collectives are launched eagerly (not graph-captured); the direct
     # communicator's are captured with the rest of the step
-    use_graph = args.impl == "ours" and not args.no_graph and (world == 1 or comm is not None)
+    use_graph = args.impl == "ours" and not args.no_graph and (world == 1 or comm is not None or p2p is not None)
     graph = None
     if use_graph:
         try:
@@ -580,11 +620,15 @@ def main():
                 "batch": BATCH, "ctx": CTX, "layers": st.layers, "heads": H, "kv_heads": HK, "head_dim": D,
                 "block_size": PAGE, "parallelism": f"tp{tp}",
                 "l2": "inputs larger than L2: 541 MB of KV per layer, 17.3 GB per step, distinct per layer",
-                "launch": ("cuda graph replay" + (" (NCCL all-reduces captured in the graph)" if comm is not None else "")
+                "launch": ("cuda graph replay" + (" (NCCL all-reduces captured in the graph)" if comm is not None else
+                                                  " (peer-to-peer all-reduce kernels captured in the graph)" if p2p is not None else "")
                            if graph is not None else
                            "one cuda graph per layer + eager NCCL all-reduce" if layer_graphs is not None else
                            "eager, one host thread") +
                           (", programmatic dependent launch" if args.impl == "ours" and not args.no_pdl else ""),
+                "all_reduce": (None if tp == 1 else
+                               "atoma_allreduce_sum_p2p (one-shot kernel over NVLink peer memory)" if p2p is not None else
+                               "ncclAllReduce (direct binding)" if comm is not None else "torch.distributed.all_reduce (NCCL)"),
                 "gemm": "atoma tcgen05 kernel" if gemm == "atoma" else "cuBLAS via torch.matmul (library GEMM, as in the reference)",
                 "wall_ms_per_step": t_wall * 1e3 / args.steps,
             },
@@ -604,6 +648,8 @@ def main():
             if t:
                 line["roofline"]["traffic"] = t["bytes"]
                 line["roofline"]["traffic_source"] = t["file"] + " (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, same inputs)"
+        if args.emulate_tp:
+            line["diagnostic"] = f"one rank's shard of a tp{tp} step on one GPU, no all-reduce: NOT a bench value"
         if args.impl == "reference":
             line["impl"] = "reference"
             line["value"] = line["e2e"]["value"]   # the reference's number is host-timed by definition
@@ -617,12 +663,16 @@ def main():
                           "(model_executor.rs:331-347); the reference has no CPU implementation of this path"}
         elif not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.barrier()
         torch.cuda.synchronize()
+        run = graph = None   # the graph holds the captured collectives: drop it before the communicator
+        if p2p is not None:
+            p2p.check()
+            p2p.destroy()
         if comm is not None:
-            run = graph = None   # the graph holds the captured collectives: drop it before the communicator
             comm.destroy()
         dist.destroy_process_group()
 

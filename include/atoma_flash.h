@@ -160,6 +160,35 @@ void atoma_gemm_bf16_tn(const void *x, const void *w, void *y, int64_t T, int64_
                         int64_t ldx, int64_t ldw, int64_t ldy, atoma_stream_t stream);
 
 /*
+ * One-shot all-reduce(sum) over NVLink peer memory for the tensor-parallel path.
+ * The reference calls NCCL through cudarc (`comm.all_reduce(src, &mut dst, &ReduceOp::Sum)`,
+ * models/src/multi_gpu.rs:141-179; one communicator per GPU thread) for the [T, hidden] payload after
+ * o_proj / down_proj; these entries serve the same call behind `AllReduce::cuda_fwd`.
+ *
+ * Every rank owns one REGION (atoma_p2p_region_bytes(slot_bytes): a header of flags and epochs plus
+ * two data slots), allocated with atoma_p2p_alloc, exported as a 64-byte CUDA IPC handle
+ * (atoma_p2p_export), exchanged out of band like the NCCL unique id, and mapped by every peer
+ * (atoma_p2p_import).  regions[r] is rank r's region as seen from THIS process (own rank: the local
+ * pointer).  The producer writes its addend into atoma_p2p_slot(regions[rank], slot_bytes, slot);
+ * atoma_allreduce_sum_p2p then leaves sum_r slot_r in `out` (local, 16-byte aligned, must not alias a
+ * slot), added in fp32 in rank order and rounded once, bit-identical on every rank.  Consecutive
+ * all-reduces of a communicator MUST alternate slot 0 / 1; every rank must make the same calls in
+ * the same order with the same count.  Stream-ordered, no host synchronisation, graph-capturable.
+ * dtype: 0 = f16, 1 = bf16, 2 = f32; world 2, 4 or 8.  A peer that does not arrive within 2 s sets
+ * the region's error word (atoma_p2p_error != 0; it synchronises the stream) instead of hanging.
+ */
+int64_t atoma_p2p_region_bytes(int64_t slot_bytes);
+int atoma_p2p_alloc(void **ptr, int64_t bytes);
+int atoma_p2p_free(void *ptr);
+int atoma_p2p_export(void *ptr, void *handle64);
+int atoma_p2p_import(const void *handle64, void **peer_ptr);
+int atoma_p2p_close(void *peer_ptr);
+void *atoma_p2p_slot(void *region, int64_t slot_bytes, int slot);
+int atoma_p2p_error(void *region, atoma_stream_t stream);
+void atoma_allreduce_sum_p2p(void *const *regions, int rank, int world, int64_t slot_bytes, int slot,
+                             void *out, int64_t count, uint32_t dtype, atoma_stream_t stream);
+
+/*
  * Process-wide launch mode, a bit set (default 0):
  *   ATOMA_LAUNCH_PDL (1)           launch this library's kernels with programmatic dependent launch:
  *                                  a kernel's prologue (barrier / TMEM / descriptor set-up) overlaps

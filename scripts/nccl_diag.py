@@ -52,6 +52,39 @@ def main():
               f"all-reduce 256KiB in graph: {us:.2f} us", flush=True)
         del gr
     comm.destroy()
+    # ---- this library's one-shot all-reduce over peer memory ----
+    from atoma_infer_b200.p2p import P2PComm
+    from atoma_infer_b200 import ops
+    p2p = P2PComm.from_torch_distributed(dev, 32 * 4096 * 2)
+    out = torch.empty((32, 4096), dtype=torch.bfloat16, device=dev)
+    for i in range(2):
+        p2p.slot(i, (32, 4096), torch.bfloat16).copy_(parts[rank].to(dev))
+    for pdl in (False, True):
+        ops.set_launch_mode(pdl=pdl, const_weights=pdl)
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            for i in range(2):
+                p2p.all_reduce(i, out)
+        s.synchronize()
+        got = out.float().cpu()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s):
+            for i in range(64):
+                p2p.all_reduce(i % 2, out)
+        gr.replay(); torch.cuda.synchronize()
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            gr.replay()
+        b.record(); torch.cuda.synchronize()
+        us = a.elapsed_time(b) * 1e3 / (5 * 64)
+        print(f"[r{rank}] p2p one-shot (pdl={pdl}): mismatches vs RN(fp32 sum)={int((got != want).sum())}/{got.numel()} "
+              f"all-reduce 256KiB in graph: {us:.2f} us", flush=True)
+        del gr
+    ops.set_launch_mode(pdl=False, const_weights=False)
+    p2p.check()
+    p2p.destroy()
     dist.destroy_process_group()
 
 

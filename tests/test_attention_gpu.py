@@ -153,6 +153,12 @@ def _decode_case(B, H, HK, D, page, MB, lens, dtype, seed, scale=None, extra_blo
     (3, 16, 16, 128, 16, 5, torch.bfloat16),   # MHA (G = 1), two head groups
     (2, 24, 12, 64, 48, 4, torch.bfloat16),    # 12 kv heads -> tiles of 4; page not a power of two
     (2, 32, 2, 128, 64, 3, torch.bfloat16),    # G = 16
+    # Llama-3.1-8B tensor-parallel shards (Hkv = 8 / tp) at long context: every sequence is split over
+    # many CTAs, the token-slice warps of a kv head are merged inside the CTA first
+    (8, 16, 4, 128, 16, 96, torch.bfloat16),   # tp2
+    (8, 8, 2, 128, 16, 128, torch.bfloat16),   # tp4
+    (8, 4, 1, 128, 16, 128, torch.bfloat16),   # tp8
+    (6, 8, 1, 64, 16, 64, torch.float16),      # one kv head, D = 64 (4-D tensor map path)
 ])
 def test_decode_paged_vs_oracle(B, H, HK, D, page, MB, dtype):
     rng = np.random.default_rng(B * 1000 + H)
