@@ -142,6 +142,7 @@ SIGNATURES = {
     "atoma_p2p_error": (C.c_int, [C.c_void_p, C.c_void_p]),
     "atoma_allreduce_sum_p2p": (None, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p,
                                        C.c_int64, C.c_uint32, C.c_void_p]),
+    "atoma_debug_allreduce_algo": (None, [C.c_int]),
     "atoma_debug_decode_trace": (None, [C.c_void_p]),
     "atoma_debug_gemm_trace": (None, [C.c_void_p]),
     "atoma_debug_gemm_stages": (None, [C.c_int]),

@@ -67,6 +67,7 @@ def parse():
                          "the step's stream (atoma_infer_b200/nccl.py); both are captured with the step in one CUDA graph; "
                          "'torch' = torch.distributed.all_reduce launched eagerly between per-layer graphs")
     ap.add_argument("--gemm", default="auto", choices=["auto", "atoma", "cublas"])
+    ap.add_argument("--ar-algo", type=int, default=0, help="diagnostics: 1 = one-shot, 2 = two-shot peer-to-peer all-reduce (0 = library's choice)")
     ap.add_argument("--emulate-tp", type=int, default=0,
                     help="diagnostics, one GPU: run ONE rank's shard of a tensor-parallel degree-N step (no all-reduce); "
                          "the JSON line is marked and is not a bench value")
@@ -416,6 +417,7 @@ def main():
                 p2p.destroy()
             p2p, tp_comm = None, "nccl"
         else:
+            _lib.lib().atoma_debug_allreduce_algo(args.ar_algo)
             st.tp_slots = [p2p.slot(i, (BATCH, HIDDEN), torch.bfloat16) for i in range(2)]
             st.tp_out = [torch.empty((BATCH, HIDDEN), device=dev, dtype=torch.bfloat16) for _ in range(2)]
             mark("peer-to-peer all-reduce regions mapped")

@@ -187,6 +187,9 @@ void *atoma_p2p_slot(void *region, int64_t slot_bytes, int slot);
 int atoma_p2p_error(void *region, atoma_stream_t stream);
 void atoma_allreduce_sum_p2p(void *const *regions, int rank, int world, int64_t slot_bytes, int slot,
                              void *out, int64_t count, uint32_t dtype, atoma_stream_t stream);
+/* Diagnostics: 0 = library's choice (default: one-shot), 1 = one-shot (every addend to every rank),
+ * 2 = two-shot (addends to the vector's owner, finished vectors back).  Same results either way. */
+void atoma_debug_allreduce_algo(int algo);
 
 /*
  * Process-wide launch mode, a bit set (default 0):

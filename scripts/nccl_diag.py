@@ -59,7 +59,9 @@ def main():
     out = torch.empty((32, 4096), dtype=torch.bfloat16, device=dev)
     for i in range(2):
         p2p.slot(i, (32, 4096), torch.bfloat16).copy_(parts[rank].to(dev))
-    for pdl in (False, True):
+    from atoma_infer_b200 import _lib
+    for algo, pdl in ((1, False), (1, True), (2, False), (2, True)):
+        _lib.lib().atoma_debug_allreduce_algo(algo)
         ops.set_launch_mode(pdl=pdl, const_weights=pdl)
         s = torch.cuda.Stream()
         with torch.cuda.stream(s):
@@ -79,7 +81,7 @@ def main():
             gr.replay()
         b.record(); torch.cuda.synchronize()
         us = a.elapsed_time(b) * 1e3 / (5 * 64)
-        print(f"[r{rank}] p2p one-shot (pdl={pdl}): mismatches vs RN(fp32 sum)={int((got != want).sum())}/{got.numel()} "
+        print(f"[r{rank}] p2p {'one' if algo == 1 else 'two'}-shot (pdl={pdl}): mismatches vs RN(fp32 sum)={int((got != want).sum())}/{got.numel()} "
               f"all-reduce 256KiB in graph: {us:.2f} us", flush=True)
         del gr
     ops.set_launch_mode(pdl=False, const_weights=False)

@@ -42,17 +42,28 @@ def _worker(rank, world, port, out_dir):
     from atoma_infer_b200.p2p import P2PComm, P2PError
     shape = (32, 4096)
     comm = P2PComm.from_torch_distributed(dev, 32 * 4096 * 4)
+    from atoma_infer_b200 import _lib
     bad = []
     k = 0
-    for dtype in (torch.bfloat16, torch.float16, torch.float32):
-        out = torch.empty(shape, dtype=dtype, device=dev)
-        for it in range(6):     # eager, alternating slots
-            parts = _addends(world, shape, dtype, it)
-            comm.slot(k % 2, shape, dtype).copy_(parts[rank].to(dev))
-            comm.all_reduce(k % 2, out)
-            k += 1
-            if not torch.equal(out.cpu(), _want(parts, dtype)):
-                bad.append(("eager", str(dtype), it))
+    for algo in (1, 2, 0):      # one-shot, two-shot, library's choice
+        _lib.lib().atoma_debug_allreduce_algo(algo)
+        for dtype in (torch.bfloat16, torch.float16, torch.float32):
+            out = torch.empty(shape, dtype=dtype, device=dev)
+            for it in range(4):     # eager, alternating slots
+                parts = _addends(world, shape, dtype, it)
+                comm.slot(k % 2, shape, dtype).copy_(parts[rank].to(dev))
+                comm.all_reduce(k % 2, out)
+                k += 1
+                if not torch.equal(out.cpu(), _want(parts, dtype)):
+                    bad.append(("eager", algo, str(dtype), it))
+        # ragged size: 1000 elements (2000 bytes = 125 vectors, not a multiple of the world size)
+        parts = _addends(world, (1000,), torch.bfloat16, 70 + algo)
+        o2 = torch.empty((1000,), dtype=torch.bfloat16, device=dev)
+        comm.slot(k % 2, (1000,), torch.bfloat16).copy_(parts[rank].to(dev))
+        comm.all_reduce(k % 2, o2)
+        k += 1
+        if not torch.equal(o2.cpu(), _want(parts, torch.bfloat16)):
+            bad.append(("ragged", algo))
     # ragged size: 1000 elements (2000 bytes, a multiple of 16)
     parts = _addends(world, (1000,), torch.bfloat16, 77)
     o2 = torch.empty((1000,), dtype=torch.bfloat16, device=dev)
@@ -67,7 +78,7 @@ def _worker(rank, world, port, out_dir):
         bad.append(("slot reuse accepted",))
     except P2PError:
         pass
-    # CUDA graph: 8 (copy-in, all-reduce) pairs, replayed 3 times
+    # CUDA graph: 8 (copy-in, all-reduce) pairs, replayed 3 times, once per algorithm
     dtype = torch.bfloat16
     srcs = [p[rank].to(dev) for p in (_addends(world, shape, dtype, 200 + i) for i in range(8))]
     wants = [_want(_addends(world, shape, dtype, 200 + i), dtype) for i in range(8)]
@@ -75,22 +86,25 @@ def _worker(rank, world, port, out_dir):
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g, stream=s):
-        for i in range(8):
-            comm.slot((k + i) % 2, shape, dtype).copy_(srcs[i])
-            comm.all_reduce((k + i) % 2, outs[i])
-    for rep in range(3):
-        for o in outs:
-            o.zero_()
-        g.replay()
-        torch.cuda.synchronize()
-        for i in range(8):
-            if not torch.equal(outs[i].cpu(), wants[i]):
-                bad.append(("graph", rep, i))
+    for algo in (1, 2):
+        _lib.lib().atoma_debug_allreduce_algo(algo)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for i in range(8):
+                comm.slot((k + i) % 2, shape, dtype).copy_(srcs[i])
+                comm.all_reduce((k + i) % 2, outs[i])
+        for rep in range(3):
+            for o in outs:
+                o.zero_()
+            g.replay()
+            torch.cuda.synchronize()
+            for i in range(8):
+                if not torch.equal(outs[i].cpu(), wants[i]):
+                    bad.append(("graph", algo, rep, i))
+        del g
+    _lib.lib().atoma_debug_allreduce_algo(0)
     comm.check()
     torch.save(bad, os.path.join(out_dir, f"r{rank}.pt"))
-    del g
     comm.destroy()
     dist.destroy_process_group()
 
