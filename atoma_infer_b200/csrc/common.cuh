@@ -46,9 +46,10 @@ enum : int { kWorkspaceDecode = 0, kWorkspaceSwapMap = 1, kWorkspaceGemm = 2, kW
 void *get_workspace(cudaStream_t stream, size_t bytes, int tag);
 
 // Launch mode (process-wide, atoma_set_launch_mode): programmatic dependent launch between this
-// library's kernels, and "weights are immutable" (the GEMM may prefetch W before its grid
-// dependency resolves).
-enum : int { kLaunchPdl = 1, kLaunchConstWeights = 2 };
+// library's kernels, "weights are immutable" (the GEMM may prefetch W before its grid dependency
+// resolves) and "only the final page of a sequence is being written" (the decode kernel may stream
+// the older pages before its grid dependency resolves).
+enum : int { kLaunchPdl = 1, kLaunchConstWeights = 2, kLaunchStableCache = 4 };
 int launch_flags();
 
 #if defined(__CUDACC__)

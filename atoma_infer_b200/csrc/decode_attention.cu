@@ -73,6 +73,7 @@ struct DecodeArgs {
     int tb;          // tokens per TMA box (divides page and tok, multiple of 16)
     int g;           // query heads per kv head
     int num_ctas;
+    int early;       // PDL + ATOMA_LAUNCH_STABLE_CACHE: stream older pages before the grid dependency resolves
     int *counters;   // [b * hg], zero between launches
     float *ws_ml;    // [cta][2][8 warps][16 rows][2]
     float *ws_o;     // [cta][2][8 warps][16 rows][D]
@@ -229,9 +230,11 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
     }
     // Programmatic dependent launch: everything above overlaps the previous kernel's tail; nothing
     // below (sequence lengths, block table, q, caches, workspace, outputs) is touched before the
-    // previous kernel in the stream has completed.
+    // previous kernel in the stream has completed — except, in "stable cache" mode, what that kernel
+    // cannot be writing: lengths, block tables and every page but the final one of a sequence.  The
+    // producer warps then run up to a full ring (192 KiB per SM) ahead of the dependency.
     pdl_launch_dependents();
-    pdl_wait();
+    if (!a.early) pdl_wait();
     if (a.trace && tid == 0) {
         a.trace[blockIdx.x * 8 + 0] = sm_id();
         a.trace[blockIdx.x * 8 + 1] = t_start;
@@ -263,16 +266,20 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
     const long long units = cum[B];
     const int cta = blockIdx.x;
 
-    // Sequences without any cached token: O = 0, LSE = +inf (flash_fwd_kernel.h:543-582).
-    for (int b = cta; b < B; b += gridDim.x) {
-        if (cum[b + 1] != cum[b]) continue;
-        T *ob = static_cast<T *>(p.o) + b * p.o_bs;
-        for (int i = tid; i < p.h * (D / 8); i += kDecodeThreads) {
-            const int hh = i / (D / 8), c = i % (D / 8);
-            *reinterpret_cast<uint4 *>(ob + hh * p.o_hs + c * 8) = make_uint4(0, 0, 0, 0);
+    // Sequences without any cached token: O = 0, LSE = +inf (flash_fwd_kernel.h:543-582).  Consumer
+    // threads only: they are the ones that wait for the dependency before anything is written.
+    if (warp < kConsumerWarps) {
+        if (a.early) pdl_wait();
+        for (int b = cta; b < B; b += gridDim.x) {
+            if (cum[b + 1] != cum[b]) continue;
+            T *ob = static_cast<T *>(p.o) + b * p.o_bs;
+            for (int i = tid; i < p.h * (D / 8); i += kConsumerThreads) {
+                const int hh = i / (D / 8), c = i % (D / 8);
+                *reinterpret_cast<uint4 *>(ob + hh * p.o_hs + c * 8) = make_uint4(0, 0, 0, 0);
+            }
+            if (p.lse)
+                for (int i = tid; i < p.h; i += kConsumerThreads) p.lse[static_cast<int64_t>(b) * p.h + i] = INFINITY;
         }
-        if (p.lse)
-            for (int i = tid; i < p.h; i += kDecodeThreads) p.lse[static_cast<int64_t>(b) * p.h + i] = INFINITY;
     }
 
     // The grid was sized from the host-side upper bound of the unit count; only the first
@@ -295,6 +302,7 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
         // =========================== producer warpgroup ===========================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
         const int pw = warp - kConsumerWarps;  // ops o = 0..2*nbx-1 of a stage (K boxes, then V boxes): warp o % 4
+        bool waited = !a.early;
         long long u = u_begin;
         int b = 0;
         while (u < u_end) {
@@ -308,6 +316,11 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
             const int *bt = p.block_table + b * p.bt_bs;
             int pbase = -(1 << 30), pg_cache = 0;
             for (int s = s0; s < s0 + n; ++s) {
+                if (!waited && s == ns - 1) {
+                    // the final stage of a sequence holds the page the predecessor is writing
+                    pdl_wait();
+                    waited = true;
+                }
                 mbar_wait(&empty[stage], phase ^ 1);
                 __syncwarp();
                 const int tok0 = s * a.tok;
@@ -815,6 +828,7 @@ int try_launch_decode_paged(const MhaParams &p, bool is_bf16, int64_t max_units_
     DecodeArgs a;
     a.p = p;
     a.hkt = hkt; a.hg = hg; a.tok = tok; a.tb = tb; a.g = G;
+    a.early = (launch_flags() & (kLaunchPdl | kLaunchStableCache)) == (kLaunchPdl | kLaunchStableCache) ? 1 : 0;
     // Upper bound on units is known on the host only through seqlen_k (= pages * page size); the
     // kernel derives the real count from the device-side lengths.  Grid: one CTA per SM, but never
     // more CTAs than the upper bound of units.

@@ -301,12 +301,13 @@ def gemm_bf16_tn(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] =
     return out
 
 
-LAUNCH_PDL, LAUNCH_CONST_WEIGHTS = 1, 2
+LAUNCH_PDL, LAUNCH_CONST_WEIGHTS, LAUNCH_STABLE_CACHE = 1, 2, 4
 
 
-def set_launch_mode(pdl: bool = False, const_weights: bool = False) -> None:
+def set_launch_mode(pdl: bool = False, const_weights: bool = False, stable_cache: bool = False) -> None:
     """include/atoma_flash.h: atoma_set_launch_mode (process-wide)."""
-    _lib.lib().atoma_set_launch_mode((LAUNCH_PDL if pdl else 0) | (LAUNCH_CONST_WEIGHTS if const_weights else 0))
+    _lib.lib().atoma_set_launch_mode((LAUNCH_PDL if pdl else 0) | (LAUNCH_CONST_WEIGHTS if const_weights else 0) |
+                                     (LAUNCH_STABLE_CACHE if stable_cache else 0))
 
 
 def last_mha_path() -> str:

@@ -73,6 +73,7 @@ def parse():
                          "the JSON line is marked and is not a bench value")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true", help="progress markers on stderr")
+    ap.add_argument("--no-early-kv", action="store_true", help="do not let the decode kernel stream older pages ahead of its dependency")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch between our kernels")
     return ap.parse_args()
 
@@ -389,7 +390,10 @@ def main():
 
     if args.impl == "ours":
         # weights are immutable during a decode step: the GEMM may stream them ahead of its dependency
-        ops.set_launch_mode(pdl=not args.no_pdl, const_weights=not args.no_pdl)
+        # ... and a decode step writes only the slot of the token being decoded (each sequence's final
+        # page): the decode kernel may stream the older pages while the cache write is still running
+        ops.set_launch_mode(pdl=not args.no_pdl, const_weights=not args.no_pdl,
+                            stable_cache=not (args.no_pdl or args.no_early_kv))
     mark("init done, building state")
     if args.emulate_tp:
         if world != 1 or args.impl != "ours":
@@ -627,7 +631,8 @@ def main():
                            if graph is not None else
                            "one cuda graph per layer + eager NCCL all-reduce" if layer_graphs is not None else
                            "eager, one host thread") +
-                          (", programmatic dependent launch" if args.impl == "ours" and not args.no_pdl else ""),
+                          (", programmatic dependent launch" if args.impl == "ours" and not args.no_pdl else "") +
+                          (", early KV streaming" if args.impl == "ours" and not (args.no_pdl or args.no_early_kv) else ""),
                 "all_reduce": (None if tp == 1 else
                                "atoma_allreduce_sum_p2p (one-shot kernel over NVLink peer memory)" if p2p is not None else
                                "ncclAllReduce (direct binding)" if comm is not None else "torch.distributed.all_reduce (NCCL)"),

@@ -201,9 +201,20 @@ void atoma_debug_allreduce_algo(int algo);
  *   ATOMA_LAUNCH_CONST_WEIGHTS (2) the `w` operand of atoma_gemm_bf16_tn is never written by work
  *                                  in flight on the stream (inference weights): with PDL the GEMM
  *                                  starts streaming W into shared memory before the predecessor ends.
+ *   ATOMA_LAUNCH_STABLE_CACHE (4)  for paged decode calls (run_mha with a block table and seqlen_q == 1):
+ *                                  the work still in flight on the stream when the call is made writes
+ *                                  no sequence length, no block-table entry and no cache row other than
+ *                                  rows of each sequence's FINAL page (the slot of the token being
+ *                                  decoded: reshape_and_cache_flash / atoma_rope_reshape_and_cache just
+ *                                  before the attention call, flash_attention.rs:361 then :455; pages
+ *                                  are exclusive to a sequence while they are written — copy-on-write).
+ *                                  With PDL the decode kernel then streams all older pages while its
+ *                                  predecessor (the cache write) is still running, and waits for it
+ *                                  only before it loads q, the final page of a sequence, or writes.
  */
 #define ATOMA_LAUNCH_PDL 1
 #define ATOMA_LAUNCH_CONST_WEIGHTS 2
+#define ATOMA_LAUNCH_STABLE_CACHE 4
 void atoma_set_launch_mode(int flags);
 int atoma_get_launch_mode(void);
 

@@ -45,8 +45,8 @@ def state():
     ops.set_launch_mode(False, False)
 
 
-def _run(st, pdl, const_w, graph):
-    ops.set_launch_mode(pdl, const_w)
+def _run(st, pdl, const_w, graph, stable_cache=False):
+    ops.set_launch_mode(pdl, const_w, stable_cache)
     kv = [c.clone() for c in st["kv0"]]
     args = (st["layers"], st["x"], st["wqkv"], st["wo"], kv, st["bt"], st["lens"], st["slots"], st["H"], st["HK"], st["D"])
     if not graph:
@@ -71,8 +71,9 @@ def _run(st, pdl, const_w, graph):
 def test_chain_pdl_and_graph_variants_are_bit_identical(state):
     base, kv_base = _run(state, False, False, False)
     assert torch.isfinite(base.float()).all() and float(base.float().abs().max()) > 0
-    for (pdl, cw, graph) in [(True, False, False), (True, True, False), (False, False, True), (True, True, True)]:
-        out, kv = _run(state, pdl, cw, graph)
-        assert torch.equal(out, base), f"pdl={pdl} const_weights={cw} graph={graph}"
+    for (pdl, cw, graph, sc) in [(True, False, False, False), (True, True, False, False), (False, False, True, False),
+                                 (True, True, True, False), (True, True, False, True), (True, True, True, True)]:
+        out, kv = _run(state, pdl, cw, graph, sc)
+        assert torch.equal(out, base), f"pdl={pdl} const_weights={cw} graph={graph} stable_cache={sc}"
         for a, b in zip(kv, kv_base):
             assert torch.equal(a, b)
