@@ -76,6 +76,25 @@ class MhaPlan(C.Structure):
     ]
 
 
+class Sequence(C.Structure):
+    """struct atoma_sequence"""
+
+    _fields_ = [("token_ids", C.POINTER(C.c_uint32)), ("length", C.c_int64), ("num_computed_tokens", C.c_int64),
+                ("token_chunk_size", C.c_int64), ("block_table", C.POINTER(C.c_uint32)), ("num_blocks", C.c_int64),
+                ("is_prompt", C.c_int32)]
+
+
+class ModelInputLayout(C.Structure):
+    """struct atoma_model_input_layout"""
+
+    _fields_ = [(n, C.c_int64) for n in (
+        "total_bytes", "input_tokens_off", "input_positions_off", "slot_mapping_off", "sequence_lengths_off",
+        "context_lengths_off", "sequence_start_loc_off", "query_start_loc_off", "block_tables_off",
+        "num_tokens", "num_slots", "num_sequences", "max_block_table_len",
+        "num_prefills", "num_prefill_tokens", "num_decode_tokens",
+        "max_query_len", "max_prefill_seq_len", "max_decode_seq_len")]
+
+
 class AttentionConfig(C.Structure):
     _fields_ = [
         ("num_heads", C.c_int64), ("num_kv_heads", C.c_int64), ("head_dim", C.c_int64),
@@ -170,6 +189,8 @@ SIGNATURES = {
                                        C.POINTER(Tensor), C.c_void_p, C.c_void_p]),
     "atoma_swap_blocks": (C.c_char_p, [C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(C.c_int64),
                                        C.POINTER(C.c_int64), C.c_int64, C.c_void_p]),
+    "atoma_prepare_input": (C.c_char_p, [C.POINTER(Sequence), C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                         C.POINTER(ModelInputLayout), C.c_void_p, C.c_int64]),
     "atoma_flash_attention_forward": (C.c_char_p, [C.POINTER(AttentionConfig)] + [C.POINTER(Tensor)] * 5 +
                                       [C.POINTER(AttentionMetadata), C.POINTER(Tensor), C.c_void_p]),
 }

@@ -82,7 +82,10 @@ def parse():
 # clocks (B200_PROFILING.md: sample nvidia-smi DURING the timed region)
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi in loop mode (20 ms period), started before the warm-up so that the process is up when
+    the timed region begins; only samples whose timestamp falls inside [t_start, t_end] (the timed
+    regions) are used."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -92,10 +95,10 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(device_index)],
+                                          "-lms", "20", "-i", str(device_index)],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
 
-    def stop(self):
+    def stop(self, t_start: float, t_end: float):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -103,28 +106,29 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        import datetime
+        inside, everything = [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in open(self.path):
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rec = (float(f[1]), float(f[2]), [n for n, v in zip(names, f[5:9]) if v.lower() == "active"])
             except ValueError:
                 continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower() == "active":
-                    reasons.add(n)
+            everything.append(rec)
+            if t_start - 0.02 <= ts <= t_end + 0.02:
+                inside.append(rec)
         os.unlink(self.path)
-        if not sm:
+        used, where = (inside, "timed regions") if inside else (everything[-10:], "warm-up + timed regions (no sample fell inside the timed window)")
+        if not used:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm.sort()
-        # "under load": the upper half of the samples (the sampler also sees the idle edges)
-        load = sm[len(sm) // 2:]
-        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        sm = sorted(r[0] for r in used)
+        reasons = sorted({n for r in used for n in r[2]})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[1] for r in used), "reasons": reasons,
+                "samples": len(used), "window": where}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -162,23 +166,44 @@ class State:
         inv = 1.0 / (500000.0 ** (torch.arange(0, D, 2, dtype=torch.float32) / D))
         ang = torch.arange(CTX + PAGE, dtype=torch.float32)[:, None] * inv[None, :]
         self.cos, self.sin = ang.cos().to(bf).to(dev), ang.sin().to(bf).to(dev)
-        # pinned host copies (the step's inputs) and their device images
-        self.host = {"x": x.pin_memory(), "bt": perm.pin_memory(), "lens": lens.pin_memory(),
-                     "slots": slots.pin_memory(), "pos": last.clone().pin_memory()}
-        self.devt = {k: v.to(dev) for k, v in self.host.items()}
+        # The step's inputs.  Hidden states: a pinned host tensor and its device image.  Metadata
+        # (block tables, sequence lengths, slot mapping, positions): built from the scheduler's view of
+        # the 32 sequences by the C++ restatement of ModelWorker::prepare_input_tensors into ONE pinned
+        # buffer and shipped with ONE copy (atoma_infer_b200/worker.py); the device
+        # tensors below are views of that buffer's device image.
+        from atoma_infer_b200.worker import InputStager, SequenceInput
+        import numpy as np
+        self.stager = InputStager(dev, PAGE)
+        rngt = np.random.default_rng(5)
+        self.seqs = [SequenceInput(rngt.integers(0, 128256, size=CTX).astype(np.uint32), 0, 1,
+                                   perm[b].numpy().astype(np.uint32), False) for b in range(BATCH)]
+        self.marshalled = self.stager.marshal(self.seqs)
+        mi = self.stager.prepare_marshalled(self.marshalled)
+        md = mi.attention_metadata
+        self.meta_bytes = int(mi.layout.total_bytes)
+        self.host = {"x": x.pin_memory()}
+        self.devt = {"x": x.to(dev), "bt": md.decoding_metadata.block_tables,
+                     "lens": md.decoding_metadata.sequence_lengths, "slots": md.slot_mapping,
+                     "pos": mi.input_positions[0]}
+        torch.cuda.synchronize()
+        assert torch.equal(self.devt["slots"].cpu(), slots) and torch.equal(self.devt["pos"].cpu(), last)
+        assert torch.equal(self.devt["bt"].cpu(), perm) and torch.equal(self.devt["lens"].cpu(), lens)
         self.out = torch.empty((BATCH, HIDDEN), device=dev, dtype=bf)
         self.out_host = torch.empty((BATCH, HIDDEN), dtype=bf).pin_memory()
         self.scale = D ** -0.5
 
     def h2d_bytes(self):
-        return sum(t.numel() * t.element_size() for t in self.host.values())
+        return self.host["x"].numel() * self.host["x"].element_size() + self.meta_bytes
 
     def d2h_bytes(self):
         return self.out_host.numel() * self.out_host.element_size()
 
     def upload(self):
-        for k, v in self.host.items():
-            self.devt[k].copy_(v, non_blocking=True)
+        """Per step: hidden states (one copy) + the step's metadata, rebuilt on the host and shipped
+        with one copy."""
+        self.devt["x"].copy_(self.host["x"], non_blocking=True)
+        lay = self.stager.refresh(self.marshalled)
+        assert lay.total_bytes == self.meta_bytes   # same shapes -> the views taken at start-up stay valid
 
     def download(self):
         self.out_host.copy_(self.out, non_blocking=True)
@@ -499,15 +524,18 @@ def main():
             layer_graphs = None
             run = step
             torch.cuda.synchronize()
-    for _ in range(max(args.warmup, 3)):
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    # Untimed: W warm-up steps, then a fixed number of extra steps (the same on every rank: the step
+    # holds collectives) that keep the GPU under the step's load while nvidia-smi comes up.
+    for _ in range(max(args.warmup, 3) + (100 if args.impl == "ours" else 20)):
         run()
     barrier()
     mark("warm-up done")
 
     # ---- timed region 1: device-resident inputs, K steps, CUDA events ----
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_clock0 = time.time()
     t_wall0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
@@ -534,7 +562,7 @@ def main():
     barrier()
     t_e2e_wall = time.perf_counter() - t0
     ms_e2e = max(e2.elapsed_time(e3), t_e2e_wall * 1e3)  # host wall-clock includes the syncs
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_clock0, time.time()) if sampler else None
     mark("timed region 2 done")
 
     # ---- dominant kernel alone: paged decode attention, one launch per layer (distinct caches) ----

@@ -177,6 +177,49 @@ const char *atoma_flash_attention_forward(const atoma_attention_config *cfg, con
                                           const atoma_attention_metadata *md,
                                           const atoma_tensor *out, atoma_stream_t stream);
 
+/*
+ * Step input preparation — `ModelWorker::prepare_input_tensors`
+ * (backends/vllm/src/worker.rs:224-460), SURVEY §8 row f2.  One flattened entry per sequence of
+ * the scheduled sequence groups (group fields repeated per sequence), in the order the reference
+ * iterates them.  Every tensor of the step's `ModelInput` / `FlashAttentionMetadata` is laid out in
+ * ONE host buffer (16-byte aligned sections, offsets in `atoma_model_input_layout`), so one
+ * host-to-device copy ships the whole step; device tensors are views at the same offsets.
+ */
+typedef struct atoma_sequence {
+    const uint32_t *token_ids;   /* sequence_data.get_token_ids(): prompt + generated tokens */
+    int64_t length;              /* sequence_data.length() */
+    int64_t num_computed_tokens; /* sequence_data.get_num_computed_tokens() (prompts only) */
+    int64_t token_chunk_size;    /* sequence_group_metadata.token_chunk_size */
+    const uint32_t *block_table; /* physical block numbers; NULL = the group has no block tables
+                                    (memory profiling run, worker.rs:365-371) */
+    int64_t num_blocks;
+    int32_t is_prompt;           /* sequence_group_metadata.is_prompt */
+} atoma_sequence;
+
+typedef struct atoma_model_input_layout {
+    int64_t total_bytes;
+    int64_t input_tokens_off;       /* u32 [num_tokens]              ModelInput::input_tokens_tensor */
+    int64_t input_positions_off;    /* i64 [num_tokens]              ModelInput::input_positions */
+    int64_t slot_mapping_off;       /* i64 [num_slots]               FlashAttentionMetadata::slot_mapping */
+    int64_t sequence_lengths_off;   /* u32 [num_sequences]           sequence_lengths (window-capped for decodes) */
+    int64_t context_lengths_off;    /* u32 [num_sequences]           context_lengths */
+    int64_t sequence_start_loc_off; /* u32 [num_sequences + 1]       cumulative sequence lengths */
+    int64_t query_start_loc_off;    /* u32 [num_sequences + 1]       cumulative query lengths */
+    int64_t block_tables_off;       /* u32 [num_sequences, max_block_table_len], padded with 0 */
+    int64_t num_tokens, num_slots, num_sequences, max_block_table_len;
+    int64_t num_prefills, num_prefill_tokens, num_decode_tokens;
+    int64_t max_query_len, max_prefill_seq_len, max_decode_seq_len;
+} atoma_model_input_layout;
+
+/* sliding_window: 0 = none.  With buffer == NULL only `layout` (sizes, offsets, scalars) is
+ * computed; otherwise `buffer` (host memory of at least layout->total_bytes, ideally pinned) is
+ * filled as well.  Returns NULL or an error text (the reference's where it has one: "Empty prompts
+ * should not be received in `ModelWorker`", "Block table should be allocated for sequence on
+ * decoding phase"). */
+const char *atoma_prepare_input(const atoma_sequence *seqs, int64_t num_sequences, int64_t block_size,
+                                int64_t sliding_window, int enable_chunked_prefill,
+                                atoma_model_input_layout *layout, void *buffer, int64_t buffer_bytes);
+
 #ifdef __cplusplus
 }
 #endif
