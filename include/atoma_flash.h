@@ -203,8 +203,9 @@ void atoma_debug_allreduce_algo(int algo);
  *                                  starts streaming W into shared memory before the predecessor ends.
  *   ATOMA_LAUNCH_STABLE_CACHE (4)  for paged decode calls (run_mha with a block table and seqlen_q == 1):
  *                                  the work still in flight on the stream when the call is made writes
- *                                  no sequence length, no block-table entry and no cache row other than
- *                                  rows of each sequence's FINAL page (the slot of the token being
+ *                                  no sequence length, no block-table entry and, in the pages this call's
+ *                                  block tables reference, no cache row other than rows of each
+ *                                  sequence's FINAL page (the slot of the token being
  *                                  decoded: reshape_and_cache_flash / atoma_rope_reshape_and_cache just
  *                                  before the attention call, flash_attention.rs:361 then :455; pages
  *                                  are exclusive to a sequence while they are written — copy-on-write).

@@ -37,6 +37,8 @@ def _sms():
     (32, 32, 8, 128, 64, torch.bfloat16),   # config 2 geometry, ctx 1024
     (16, 8, 1, 128, 64, torch.bfloat16),    # config 4 per-rank geometry (reference uses 2 splits)
     (1, 32, 8, 64, 48, torch.bfloat16),     # config 1 geometry (reference splits 3 ways)
+    (32, 16, 4, 128, 64, torch.bfloat16),   # config 2 sharded over 2 GPUs (per-rank geometry)
+    (32, 8, 2, 128, 64, torch.bfloat16),    # config 2 sharded over 4 GPUs
     (4, 32, 8, 128, 16, torch.float16),
 ])
 def test_decode_matches_reference_kernels(ref, B, H, HK, D, MB, dtype):
