@@ -163,6 +163,7 @@ SIGNATURES = {
                                        C.c_int64, C.c_uint32, C.c_void_p]),
     "atoma_debug_allreduce_algo": (None, [C.c_int]),
     "atoma_debug_decode_trace": (None, [C.c_void_p]),
+    "atoma_debug_decode_merge": (None, [C.c_int]),
     "atoma_debug_gemm_trace": (None, [C.c_void_p]),
     "atoma_debug_gemm_stages": (None, [C.c_int]),
     "atoma_set_launch_mode": (None, [C.c_int]),

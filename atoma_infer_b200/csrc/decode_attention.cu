@@ -74,6 +74,7 @@ struct DecodeArgs {
     int g;           // query heads per kv head
     int num_ctas;
     int early;       // PDL + ATOMA_LAUNCH_STABLE_CACHE: stream older pages before the grid dependency resolves
+    int merged;      // map_k describes K AND V (one allocation, contiguous heads): one op moves both
     int *counters;   // [b * hg], zero between launches
     float *ws_ml;    // [cta][2][8 warps][16 rows][2]
     float *ws_o;     // [cta][2][8 warps][16 rows][D]
@@ -341,7 +342,22 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
                         phys[bx] = __shfl_sync(0xffffffffu, pg_cache, pi - pbase);
                     }
                 }
-                if (lane == 0) {
+                if (lane == 0 && a.merged) {
+                    // K and V of a page in ONE op: box bx goes to warp bx % 4; smem [box][K|V][head][half][token]
+                    int nmine = 0;
+#pragma unroll
+                    for (int bx = 0; bx < 8; ++bx) nmine += (bx < nbx && (bx & 3) == pw) ? 1 : 0;
+                    mbar_arrive_expect_tx(&full_k[stage], nmine * 2 * box_bytes);
+#pragma unroll
+                    for (int bx = 0; bx < 8; ++bx) {
+                        if (bx < nbx && (bx & 3) == pw) {
+                            const int t_in_page = (tok0 + bx * a.tb) % p.page;
+                            tma_load_5d(ks + bx * 2 * box_bytes, &map_k, &full_k[stage], 0, t_in_page,
+                                        hg * a.hkt * C::kHalves, 0, phys[bx], kL2EvictFirst);
+                        }
+                    }
+                    mbar_arrive(&full_v[stage]);  // V came with K: nothing more to expect
+                } else if (lane == 0) {
                     // this warp's share: K box bx when bx % 4 == pw, V box bx when (nbx + bx) % 4 == pw
                     int nk = 0, nv = 0;
 #pragma unroll
@@ -393,7 +409,10 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
     const int ts = warp / a.hkt;          // 16-token slice within the stage
     const int bx_w = (ts * 16) / a.tb;    // box holding this warp's tokens
     // 128-byte line index of this warp's first token, first half: box layout [head][half][token]
-    const int row_base = bx_w * box_rows + hh * C::kHalves * a.tb + (ts * 16) % a.tb;
+    const int row_base = hh * C::kHalves * a.tb + (ts * 16) % a.tb;   // ... inside the box
+    // byte offsets of this warp's K and V boxes inside a stage
+    const uint32_t k_off = a.merged ? bx_w * 2 * box_bytes : bx_w * box_bytes;
+    const uint32_t v_off = a.merged ? k_off + box_bytes : C::kTileBytes + bx_w * box_bytes;
     const int G = a.g;
 
     long long u = u_begin;
@@ -429,8 +448,8 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
         float l_run[2] = {0.f, 0.f};
 
         for (int s = s0; s < s0 + n; ++s) {
-            const uint32_t ks = smem_u32(tiles + stage * C::kStageBytes);
-            const uint32_t vs = ks + C::kTileBytes;
+            const uint32_t ks = smem_u32(tiles + stage * C::kStageBytes) + k_off;
+            const uint32_t vs = smem_u32(tiles + stage * C::kStageBytes) + v_off;
             const int nvalid = len - (s * a.tok + ts * 16);  // valid tokens in this warp's slice
             mbar_wait(&full_k[stage], phase);
             if (nvalid > 0) {
@@ -714,7 +733,7 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
 // ---------------------------------------------------------------------------------------------
 struct MapKey {
     const void *ptr;
-    int64_t rs, hs, bs;
+    int64_t rs, hs, bs, kv_delta;
     int page, hk, d, tb, hkt, bf16;
     bool operator==(const MapKey &o) const { return std::memcmp(this, &o, sizeof(MapKey)) == 0; }
 };
@@ -723,12 +742,13 @@ struct MapEntry {
     CUtensorMap map;
 };
 
+// kv_delta > 0: ONE map over K and V (V = K + kv_delta bytes, heads contiguous: hs == d), see below.
 bool make_kv_map(CUtensorMap *out, const void *ptr, int64_t rs, int64_t hs, int64_t bs, int page,
-                 int hk, int d, int tb, int hkt, bool is_bf16) {
+                 int hk, int d, int tb, int hkt, bool is_bf16, int64_t kv_delta = 0) {
     static thread_local std::vector<MapEntry> cache;
     MapKey key;
     std::memset(&key, 0, sizeof(key));
-    key.ptr = ptr; key.rs = rs; key.hs = hs; key.bs = bs; key.page = page; key.hk = hk; key.d = d;
+    key.ptr = ptr; key.rs = rs; key.hs = hs; key.bs = bs; key.kv_delta = kv_delta; key.page = page; key.hk = hk; key.d = d;
     key.tb = tb; key.hkt = hkt; key.bf16 = is_bf16;
     for (const MapEntry &e : cache)
         if (e.key == key) { *out = e.map; return true; }
@@ -741,8 +761,22 @@ bool make_kv_map(CUtensorMap *out, const void *ptr, int64_t rs, int64_t hs, int6
     //            box {64, tb, 2, hkt, 1}: both 128-byte halves of every row in one op, landing as
     //            [head][half][token] lines (token & 7 stays the swizzle phase of a line).
     const CUtensorMapDataType dt = is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    //   K and V in one allocation with contiguous heads (the reference's [2, NB, bs, Hkv, D] cache):
+    //            {64 d, token-in-page, 128-byte line of the token row (= head x half, stride 128 B),
+    //             K|V (stride V - K), physical page}, box {64, tb, lines of hkt heads, 2, 1}: K AND V
+    //            of hkt heads of a page in one op, landing as [K|V][head][half][token] lines.
     CUresult r;
-    if (d == 128) {
+    if (kv_delta > 0) {
+        const int halves = d / 64;
+        const cuuint64_t dims[5] = {64, static_cast<cuuint64_t>(page), static_cast<cuuint64_t>(hk * halves), 2,
+                                    static_cast<cuuint64_t>(1) << 22};
+        const cuuint64_t strides[4] = {static_cast<cuuint64_t>(rs) * 2, 128, static_cast<cuuint64_t>(kv_delta),
+                                       static_cast<cuuint64_t>(bs) * 2};
+        const cuuint32_t box[5] = {64, static_cast<cuuint32_t>(tb), static_cast<cuuint32_t>(hkt * halves), 2, 1};
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        r = enc(out, dt, 5, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else if (d == 128) {
         const cuuint64_t dims[5] = {64, static_cast<cuuint64_t>(page), 2, static_cast<cuuint64_t>(hk),
                                     static_cast<cuuint64_t>(1) << 22};
         const cuuint64_t strides[4] = {static_cast<cuuint64_t>(rs) * 2, 128, static_cast<cuuint64_t>(hs) * 2,
@@ -770,7 +804,11 @@ bool make_kv_map(CUtensorMap *out, const void *ptr, int64_t rs, int64_t hs, int6
     return true;
 }
 
+// TMA box dimensions are limited to 256 elements each.
+inline bool box_lines_ok(int hkt, int d) { return hkt * (d / 64) <= 256; }
+
 void *g_decode_trace = nullptr;
+int g_decode_no_merge = 0;  // diagnostics (atoma_debug_decode_merge): 1 = always two tensor maps
 
 template <typename T, int D>
 bool launch_decode(const CUtensorMap &mk, const CUtensorMap &mv, const DecodeArgs &a,
@@ -846,9 +884,21 @@ int try_launch_decode_paged(const MhaParams &p, bool is_bf16, int64_t max_units_
     a.ws_o = reinterpret_cast<float *>(ws + counters_bytes + ml_bytes);
     a.trace = static_cast<unsigned long long *>(g_decode_trace);
 
+    // K and V views of one [2, NB, bs, Hkv, D] allocation (flash_attention.rs:239-246, 274-275): one
+    // tensor map over both, one op per page for K and V together (op size x2 — what decides the
+    // per-SM bandwidth of tensor-parallel shards, see the header).  Anything else: two maps.
+    const int64_t kv_delta = static_cast<const char *>(p.v) - static_cast<const char *>(p.k);
+    const bool merged = p.k_hs == p.d && p.v_hs == p.d && p.k_rs == p.v_rs && p.k_bs == p.v_bs && kv_delta > 0 &&
+                        kv_delta % 16 == 0 && kv_delta < (1ll << 40) && box_lines_ok(hkt, p.d) && !g_decode_no_merge;
+    a.merged = merged ? 1 : 0;
     CUtensorMap mk, mv;
-    if (!make_kv_map(&mk, p.k, p.k_rs, p.k_hs, p.k_bs, p.page, p.h_k, p.d, tb, hkt, is_bf16)) return -1;
-    if (!make_kv_map(&mv, p.v, p.v_rs, p.v_hs, p.v_bs, p.page, p.h_k, p.d, tb, hkt, is_bf16)) return -1;
+    if (merged) {
+        if (!make_kv_map(&mk, p.k, p.k_rs, p.k_hs, p.k_bs, p.page, p.h_k, p.d, tb, hkt, is_bf16, kv_delta)) return -1;
+        mv = mk;
+    } else {
+        if (!make_kv_map(&mk, p.k, p.k_rs, p.k_hs, p.k_bs, p.page, p.h_k, p.d, tb, hkt, is_bf16)) return -1;
+        if (!make_kv_map(&mv, p.v, p.v_rs, p.v_hs, p.v_bs, p.page, p.h_k, p.d, tb, hkt, is_bf16)) return -1;
+    }
 
     bool ok;
     if (is_bf16) ok = p.d == 128 ? launch_decode<__nv_bfloat16, 128>(mk, mv, a, stream)
@@ -859,5 +909,6 @@ int try_launch_decode_paged(const MhaParams &p, bool is_bf16, int64_t max_units_
 }
 
 void set_decode_trace(void *device_buf) { g_decode_trace = device_buf; }
+void set_decode_merge(int enable) { g_decode_no_merge = enable ? 0 : 1; }
 
 }  // namespace atoma

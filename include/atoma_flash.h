@@ -224,6 +224,9 @@ int atoma_get_launch_mode(void);
  * reduction started, reduction finished} (globaltimer ns; the last two only on CTAs that reduce)
  * at device_buf[8*cta..]; the buffer must hold 8 * #SM entries.  NULL switches it off (default). */
 void atoma_debug_decode_trace(void *device_buf);
+/* Diagnostics: 0 = the decode kernel always uses separate K and V tensor maps (two ops per page);
+ * 1 (default) = one map and one op for K and V when they are views of one allocation. */
+void atoma_debug_decode_merge(int enable);
 /* Same for the projection GEMM: {start, first operand tile landed, last accumulator complete, end}. */
 void atoma_debug_gemm_trace(void *device_buf);
 /* Diagnostics: cap the GEMM's shared-memory ring at `stages` stages (0 = as many as fit). */

@@ -57,6 +57,9 @@ def main():
     def ours(i):
         L.atoma_mha_execute(C.byref(plans[i % nrot]), out.data_ptr(), None, None, None, 0, stream)
 
+    if os.environ.get("ATOMA_MB_NO_MERGE"):
+        L.atoma_debug_decode_merge(0)
+        res["merge"] = False
     med, best = time_it(ours)
     res["ours_us_median"] = med * 1e6
     res["ours_us_best"] = best * 1e6

@@ -169,6 +169,39 @@ def test_decode_paged_vs_oracle(B, H, HK, D, page, MB, dtype):
     assert_close_16(t2f32(out), want, is_bf16, f"decode B={B} H={H} HK={HK} D={D} page={page}")
 
 
+@pytest.mark.parametrize("HK,order", [(8, "separate"), (8, "v_first"), (1, "separate"), (4, "no_merge")])
+def test_decode_k_and_v_in_separate_allocations(HK, order):
+    """The kernel uses ONE tensor map (one op per page for K and V) when K and V are the two halves of
+    one allocation, as in the reference's [2, NB, bs, Hkv, D] cache; separate allocations, V below
+    K, or the diagnostic switch take the two-map path.  All must give the same bits."""
+    from atoma_infer_b200 import _lib
+    B, G, D, page, MB = 4, 4, 128, 16, 40
+    H = HK * G
+    NB = B * MB + 3
+    rng = np.random.default_rng(HK)
+    lens = rng.integers(1, MB * page + 1, size=B).tolist()
+    lens[0] = MB * page
+    kv = randn_t((2, NB, page, HK, D), 61, torch.bfloat16, DEV)
+    q = randn_t((B, 1, H, D), 62, torch.bfloat16, DEV)
+    bt = random_block_table(B, MB, NB, 63, DEV)
+    base = ops.flash_attn_kv_cache_full(q, kv[0], kv[1], None, D ** -0.5, bt, u32(lens), True)
+    if order == "separate":
+        k, v = kv[0].clone(), kv[1].clone()
+    elif order == "v_first":
+        both = torch.empty_like(kv)
+        both[1].copy_(kv[0]); both[0].copy_(kv[1])
+        k, v = both[1], both[0]            # V lies below K in memory
+    else:
+        k, v = kv[0], kv[1]
+        _lib.lib().atoma_debug_decode_merge(0)
+    try:
+        out = ops.flash_attn_kv_cache_full(q, k, v, None, D ** -0.5, bt, u32(lens), True)
+    finally:
+        _lib.lib().atoma_debug_decode_merge(1)
+    assert ops.last_mha_path() == "decode_paged"
+    assert torch.equal(out, base)
+
+
 def test_decode_ragged_empty_and_single_token():
     """Edge cases of SURVEY appendix B: len 0 -> zeros, len 1, ragged tails in the first / last page,
     a length one short of and exactly at a stage boundary."""
