@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(kArThreads) allreduce_p2p_kernel(const ArArgs 
     pdl_launch_dependents();
     pdl_wait();
     const uint32_t e = a.state[0] + 1;   // this launch's epoch; advanced by the last CTA to finish
+    if (a.state[2] != 0) return;          // a peer failed to arrive earlier: do not wait for it again
     bool failed = false;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * kArThreads + tid; i < a.nvec;
          i += static_cast<int64_t>(gridDim.x) * kArThreads) {
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(kArThreads) allreduce_p2p_twoshot_kernel(const
     pdl_launch_dependents();
     pdl_wait();
     const uint32_t e = a.state[0] + 1;
+    if (a.state[2] != 0) return;
     const int64_t chunk = (a.nvec + W - 1) / W;          // vectors per owner
     const int64_t half = a.recv_stride / 2;              // byte offset of the flight-2 area
     bool failed = false;
@@ -411,7 +413,10 @@ extern "C" void atoma_allreduce_sum_p2p(void *const *regions, int rank, int worl
     a.nvec = count * esz / 16;
     a.rank = rank;
     a.world = world;
-    a.timeout_ns = 2000000000ull;  // 2 s: a peer that never arrives must not hang the GPU
+    // A peer that never arrives must not hang the GPU; ranks of one job may legitimately reach their
+    // first all-reduce seconds apart (library initialisation), so the limit is generous and is paid
+    // once: later launches return at once when the error word is set.
+    a.timeout_ns = 30000000000ull;
     const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(kArMaxCtas, (a.nvec + kArThreads - 1) / kArThreads)));
     cudaError_t e;
     if (dtype == 1) e = launch_ar<__nv_bfloat16>(a, grid, static_cast<cudaStream_t>(stream));

@@ -102,7 +102,7 @@ class P2PComm:
         """Synchronises the current stream; raises if a peer ever failed to arrive."""
         rc = _lib.lib().atoma_p2p_error(self._local, torch.cuda.current_stream(self.device).cuda_stream)
         if rc != 0:
-            raise P2PError("a peer did not arrive at an all-reduce within 2 s" if rc == 1 else f"CUDA error {rc}")
+            raise P2PError("a peer did not arrive at an all-reduce within 30 s" if rc == 1 else f"CUDA error {rc}")
 
     def destroy(self) -> None:
         if self._local is None:

@@ -464,6 +464,12 @@ def main():
         torch.cuda.synchronize()
 
     # ---- one eager step: allocates library workspaces, warms cuBLAS; then capture ----
+    if dist is not None:
+        # library initialisation (cuBLAS handles, kernel loading, workspaces) before the first collective,
+        # so that the ranks reach it together
+        step.layer(0, st.devt["x"])
+        torch.cuda.synchronize()
+        dist.barrier()
     ops.reset_launch_count()
     step()
     torch.cuda.synchronize()

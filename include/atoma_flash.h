@@ -174,7 +174,7 @@ void atoma_gemm_bf16_tn(const void *x, const void *w, void *y, int64_t T, int64_
  * slot), added in fp32 in rank order and rounded once, bit-identical on every rank.  Consecutive
  * all-reduces of a communicator MUST alternate slot 0 / 1; every rank must make the same calls in
  * the same order with the same count.  Stream-ordered, no host synchronisation, graph-capturable.
- * dtype: 0 = f16, 1 = bf16, 2 = f32; world 2, 4 or 8.  A peer that does not arrive within 2 s sets
+ * dtype: 0 = f16, 1 = bf16, 2 = f32; world 2, 4 or 8.  A peer that does not arrive within 30 s sets
  * the region's error word (atoma_p2p_error != 0; it synchronises the stream) instead of hanging.
  */
 int64_t atoma_p2p_region_bytes(int64_t slot_bytes);
