@@ -1,0 +1,69 @@
+"""bench.py host-side helpers that run on the GPU box unattended: clock-sample parsing / windowing and
+the ncu-capture reader behind `roofline.traffic` (no GPU needed)."""
+import datetime
+import json
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import bench  # noqa: E402
+
+
+def _line(ts, sm, reasons=("Not Active",) * 4):
+    stamp = datetime.datetime.fromtimestamp(ts).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+    return f"{stamp}, {sm}, 1965, 700.0, 0x0000000000000000, " + ", ".join(reasons) + "\n"
+
+
+def _sampler(tmp_path, lines):
+    s = bench.ClockSampler.__new__(bench.ClockSampler)
+    p = tmp_path / "clk.csv"
+    p.write_text("".join(lines))
+
+    class Done:
+        def terminate(self): pass
+        def wait(self, timeout=None): return 0
+        def kill(self): pass
+    s.proc, s.path, s.dev = Done(), str(p), 0
+    return s
+
+
+def test_clock_samples_are_windowed_to_the_timed_region(tmp_path):
+    t = time.time()
+    lines = [_line(t - 1.0, 1200), _line(t + 0.1, 1965), _line(t + 0.2, 1950),
+             _line(t + 0.3, 1965, ("Not Active", "Not Active", "Not Active", "Active")), _line(t + 2.0, 300),
+             "garbage line\n"]
+    out = _sampler(tmp_path, lines).stop(t, t + 0.5)
+    assert out["samples"] == 3 and out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"] and out["window"] == "timed regions"
+
+
+def test_clock_samples_fall_back_when_the_window_is_empty(tmp_path):
+    t = time.time()
+    out = _sampler(tmp_path, [_line(t - 1.0, 1900), _line(t - 0.9, 1910)]).stop(t, t + 0.01)
+    assert out["samples"] == 2 and "no sample fell inside" in out["window"]
+    assert _sampler(tmp_path, []).stop(t, t + 1)["reasons"] == ["no samples"]
+
+
+def test_ncu_traffic_reads_the_committed_capture():
+    t = bench.ncu_traffic("decode_paged_kernel")
+    assert t is not None and t["file"].startswith("profiles/")
+    # K and V of 32 x 4096 tokens x 8 heads x 128 x 2 B once, plus q, o, block table: ~537.4 MB algorithmic
+    assert 537e6 < t["bytes"] < 1.05 * 537.5e6
+    assert bench.ncu_traffic("no_such_kernel") is None
+
+
+def test_committed_bench_lines_follow_the_contract():
+    for name in ("r01_bench_ours.json", "r01_bench_reference.json"):
+        d = json.loads((ROOT / "profiles" / name).read_text())
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+            assert k in d, (name, k)
+        assert "workload" in d["config"] and "model" not in d["config"]
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+        assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+    ref = json.loads((ROOT / "profiles" / "r01_bench_reference.json").read_text())
+    assert ref["impl"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0
