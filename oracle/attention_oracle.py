@@ -305,3 +305,39 @@ def attention_paged_decode(q: np.ndarray, k_cache: np.ndarray, v_cache: np.ndarr
     if exact:
         return ox.reshape(b, sq, h, d), lse
     return to_f32(o, is_bf16).reshape(b, sq, h, d), lse
+
+
+# ---------------------------------------------------------------------------------------------------
+# Caller-side split heuristic (csrc/src/lib.rs:2122-2199), restated with f32 arithmetic where the
+# Rust uses f32 (the 0.8 and 0.85 thresholds are compared in single precision).
+# ---------------------------------------------------------------------------------------------------
+def num_splits_heuristic(batch_nheads_mblocks: int, num_sms: int, num_n_blocks: int, max_splits: int) -> int:
+    """lib.rs:2122-2166"""
+    f = np.float32
+    if f(batch_nheads_mblocks) >= f(0.8) * f(num_sms):
+        return 1
+    max_splits = min(max_splits, num_sms, num_n_blocks)
+    ceil_div = lambda a, b: (a + b - 1) // b
+    eligible = lambda s: s == 1 or ceil_div(num_n_blocks, s) != ceil_div(num_n_blocks, s - 1)
+    eff, best = [], f(0.0)
+    for s in range(1, max_splits + 1):
+        if not eligible(s):
+            eff.append(f(0.0))
+            continue
+        n_waves = f(batch_nheads_mblocks * s) / f(num_sms)
+        e = n_waves / np.ceil(n_waves)
+        best = max(best, e)
+        eff.append(e)
+    for s in range(1, max_splits + 1):
+        if eligible(s) and eff[s - 1] >= f(0.85) * best:
+            return s
+    return 1
+
+
+def compute_num_splits(batch_size: int, num_heads: int, head_size: int, max_seqlen_k: int, max_seqlen_q: int,
+                       num_sms: int) -> int:
+    """lib.rs:2168-2199"""
+    block_n = 256 if head_size <= 64 else 128 if head_size <= 128 else 64
+    num_n_blocks = (max_seqlen_k + block_n - 1) // block_n
+    num_m_blocks = (max_seqlen_q + 63) // 64
+    return num_splits_heuristic(batch_size * num_heads * num_m_blocks, num_sms * 2, num_n_blocks, 128)

@@ -107,6 +107,23 @@ def test_compute_num_splits_cases():
     assert ops.compute_num_splits(1, 48, 128, 128 * 64, 1, 54) == 2
 
 
+def test_compute_num_splits_sweep_against_the_restated_heuristic():
+    """The C++ host layer against the oracle's restatement of lib.rs:2122-2199 on a seeded sweep that
+    covers the 0.8-occupancy shortcut, ineligible split counts and the 85 % rule."""
+    import numpy as np
+    from oracle import attention_oracle as orc
+    rng = np.random.default_rng(0)
+    seen = set()
+    for _ in range(3000):
+        b = int(rng.integers(1, 65)); h = int(rng.choice([1, 2, 4, 8, 16, 32, 40, 64]))
+        d = int(rng.choice([32, 64, 96, 128, 192, 256])); sk = int(rng.integers(1, 20000))
+        sq = int(rng.choice([1, 1, 1, 7, 64, 65, 200])); sms = int(rng.choice([54, 108, 132, 148]))
+        want = orc.compute_num_splits(b, h, d, sk, sq, sms)
+        assert ops.compute_num_splits(b, h, d, sk, sq, sms) == want, (b, h, d, sk, sq, sms)
+        seen.add(want)
+    assert len(seen) > 10 and 1 in seen
+
+
 def test_kv_cache_decode_folds_causal_only_for_single_query():
     q1 = spec([2, 1, 4, 64], BF16)
     q3 = spec([2, 3, 4, 64], BF16)
