@@ -166,6 +166,7 @@ SIGNATURES = {
     "atoma_debug_decode_merge": (None, [C.c_int]),
     "atoma_debug_gemm_trace": (None, [C.c_void_p]),
     "atoma_debug_gemm_stages": (None, [C.c_int]),
+    "atoma_debug_gemm_algo": (None, [C.c_int]),
     "atoma_set_launch_mode": (None, [C.c_int]),
     "atoma_get_launch_mode": (C.c_int, []),
     "atoma_last_status": (C.c_int, []),

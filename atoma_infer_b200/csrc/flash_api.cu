@@ -24,6 +24,7 @@ void set_decode_trace(void *device_buf);
 void set_gemm_trace(void *device_buf);
 void set_decode_merge(int enable);
 void set_gemm_stage_limit(int stages);
+void set_gemm_algo(int algo);
 bool launch_gemm_bf16_tn(const void *x, const void *w, void *y, int64_t T, int64_t N, int64_t K,
                          int64_t ldx, int64_t ldw, int64_t ldy, cudaStream_t stream);
 
@@ -294,6 +295,7 @@ extern "C" void atoma_debug_decode_trace(void *device_buf) { set_decode_trace(de
 extern "C" void atoma_debug_gemm_trace(void *device_buf) { set_gemm_trace(device_buf); }
 extern "C" void atoma_debug_decode_merge(int enable) { set_decode_merge(enable); }
 extern "C" void atoma_debug_gemm_stages(int stages) { set_gemm_stage_limit(stages); }
+extern "C" void atoma_debug_gemm_algo(int algo) { set_gemm_algo(algo); }
 extern "C" void atoma_set_launch_mode(int flags) { g_launch_flags.store(flags, std::memory_order_relaxed); }
 extern "C" int atoma_get_launch_mode(void) { return launch_flags(); }
 extern "C" int atoma_last_status(void) { return t_status; }

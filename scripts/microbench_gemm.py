@@ -45,10 +45,18 @@ def main():
             torch.cuda.synchronize()
             return a.elapsed_time(b) * 1e3 / (reps * nrot)
         t_ours = time_it(lambda i: ops.gemm_bf16_tn(x, ws[i % nrot], out=y))
+        t_cluster = None
+        if "--cluster" in sys.argv and T <= 64:   # experimental variant (atoma_debug_gemm_algo)
+            from atoma_infer_b200 import _lib
+            _lib.lib().atoma_debug_gemm_algo(1)
+            try:
+                t_cluster = time_it(lambda i: ops.gemm_bf16_tn(x, ws[i % nrot], out=y))
+            finally:
+                _lib.lib().atoma_debug_gemm_algo(0)
         t_cublas = time_it(lambda i: torch.matmul(x, ws[i % nrot].t(), out=y))
         byts = 2 * (N * K + T * K + T * N)
         flops = 2.0 * T * N * K
-        out.append({"T": T, "N": N, "K": K, "ours_us": t_ours, "cublas_us": t_cublas,
+        out.append({"T": T, "N": N, "K": K, "ours_us": t_ours, "ours_cluster_us": t_cluster, "cublas_us": t_cublas,
                     "ours_GBps": byts / t_ours / 1e3, "cublas_GBps": byts / t_cublas / 1e3,
                     "ours_TFLOPs": flops / t_ours / 1e6, "cublas_TFLOPs": flops / t_cublas / 1e6})
         print(json.dumps(out[-1]), flush=True)
