@@ -344,9 +344,9 @@ gemm_tn_stream_kernel(const __grid_constant__ CUtensorMap map_w,
 
 
 // ---------------------------------------------------------------------------------------------
-// EXPERIMENTAL (opt-in through atoma_debug_gemm_algo(1); written at the end of round 1, compiled and
-// SASS-checked but NOT yet run on hardware): fixed split per tile, reduced through distributed shared
-// memory.  The stream-K kernel above loses ~4.5 us per launch in its tail (partials through L2, fence,
+// EXPERIMENTAL (opt-in through atoma_debug_gemm_algo(1); written at the end of round 1: parity-green
+// on a B200 in its one run — o_proj 15.9 us vs 17.5 us stream-K, cuBLAS 10.1 — but not yet tuned or
+// profiled): fixed split per tile, reduced through distributed shared memory.  The stream-K kernel above loses ~4.5 us per launch in its tail (partials through L2, fence,
 // arrival counter, last-arriver reduction — scripts/trace_gemm_pair.py).  Here a thread-block cluster
 // of `csize` CTAs owns one 128-row weight tile, CTA r streams the r-th part of K, and the partial
 // accumulators of CTAs 1.. are written straight into CTA 0's shared memory (st.shared::cluster),

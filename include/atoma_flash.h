@@ -233,7 +233,7 @@ void atoma_debug_gemm_trace(void *device_buf);
 void atoma_debug_gemm_stages(int stages);
 /* Diagnostics: 0 (default) = stream-K GEMM; 1 = try the EXPERIMENTAL cluster variant first (one
  * thread-block cluster per weight tile, split reduced through distributed shared memory; decode
- * shapes only; not yet validated on hardware — the default path never takes it). */
+ * shapes only; parity-green but not yet tuned — the default path never takes it). */
 void atoma_debug_gemm_algo(int algo);
 
 /* 0 = last call on this thread succeeded; otherwise a negative atoma code or a cudaError_t. */

@@ -84,8 +84,8 @@ def test_gemm_exact_small_integers():
 
 
 @pytest.mark.skipif(__import__("os").environ.get("ATOMA_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental cluster/DSMEM GEMM variant: written at the end of round 1, compiled but not yet "
-                           "validated on hardware; set ATOMA_TEST_EXPERIMENTAL=1 to run it")
+                    reason="experimental cluster/DSMEM GEMM variant (opt-in, passed on a B200 at the end of round 1, not "
+                           "yet tuned); set ATOMA_TEST_EXPERIMENTAL=1 to run it")
 @pytest.mark.parametrize("T,N,K", [(32, 6144, 4096), (32, 4096, 4096), (16, 1280, 8192), (1, 3072, 2048),
                                    (48, 4096, 4096), (64, 6144, 4096), (5, 5000, 4040)])
 def test_gemm_cluster_variant_vs_fp64(T, N, K):
