@@ -300,6 +300,18 @@ def make_step(st: State, impl: str, gemm: str, dist, comm=None, p2p=None):
 # CPU baseline: the numpy oracle ("port") on a bounded sample of the same workload
 # ------------------------------------------------------------------------------------------------
 def cpu_baseline(seconds_budget: float = 20.0):
+    """One host thread: numpy's BLAS pool is pinned to 1 for the duration, so that `cores: 1` is what
+    actually ran (the oracle's attention loops are single-threaded anyway)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=1):
+            return _cpu_baseline(seconds_budget, "1 (BLAS pool pinned to one thread)")
+    except ImportError:
+        import os as _os
+        return _cpu_baseline(seconds_budget, f"numpy BLAS default pool (up to {_os.cpu_count()} threads) + 1 for the oracle's loops")
+
+
+def _cpu_baseline(seconds_budget: float, threads_note: str):
     import numpy as np
     from oracle import attention_oracle as orc
     rng = np.random.default_rng(0)
@@ -333,9 +345,10 @@ def cpu_baseline(seconds_budget: float = 20.0):
     dt = (time.perf_counter() - t0) / n            # seconds per layer for b sequences
     tok_s = b / (dt * L)
     del x2
-    return {"value": tok_s, "unit": "tokens/s", "cores": 1, "kind": "port",
+    return {"value": tok_s, "unit": "tokens/s", "cores": 1 if threads_note.startswith("1 ") else (os.cpu_count() or 1),
+            "kind": "port",
             "sample": f"numpy oracle (oracle/attention_oracle.py), {n} layer pass(es) of the same path for {b} of "
-                      f"the 32 sequences at ctx {CTX}; scaled to 32 layers"}
+                      f"the 32 sequences at ctx {CTX}; scaled to 32 layers; host threads: {threads_note}"}
 
 
 def ncu_traffic(kernel_substr: str):
