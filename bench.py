@@ -715,8 +715,8 @@ def main():
                 "sample": "the reference's own CUDA kernels (oracle/_ref, built from /root/reference/csrc/kernels for sm_100) "
                           "driven from ONE host thread with host wall-clock timing, as the reference times itself "
                           "(model_executor.rs:331-347); the reference has no CPU implementation of this path"}
-        elif not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline()
+        elif not args.no_cpu_baseline and world == 1 and not args.emulate_tp:
+            line["cpu_baseline"] = cpu_baseline()   # rank 0, N = 1 only: the CPU port does not change with N
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
