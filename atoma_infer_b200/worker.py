@@ -80,10 +80,11 @@ class InputStager:
             arr[i].token_chunk_size = int(s.token_chunk_size)
             if s.block_table is not None:
                 bt = _u32(s.block_table)
-                keep.append(bt)
-                # an empty table is still "allocated": keep the pointer non-NULL
-                arr[i].block_table = bt.ctypes.data_as(C.POINTER(C.c_uint32)) if bt.size else \
-                    C.cast(C.c_void_p(16), C.POINTER(C.c_uint32))
+                # an empty table is still "allocated" (NULL means "the group has no block tables"):
+                # point at a one-element dummy, num_blocks stays 0
+                buf = bt if bt.size else np.zeros(1, dtype=np.uint32)
+                keep.append(buf)
+                arr[i].block_table = buf.ctypes.data_as(C.POINTER(C.c_uint32))
                 arr[i].num_blocks = bt.size
             arr[i].is_prompt = 1 if s.is_prompt else 0
         return arr, keep
