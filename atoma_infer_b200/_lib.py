@@ -118,6 +118,35 @@ class AttentionMetadata(C.Structure):
     ]
 
 
+class LlamaLayer(C.Structure):
+    """struct atoma_llama_layer (include/atoma_llama.h)"""
+
+    _fields_ = [(n, C.c_void_p) for n in ("wqkv", "wo", "w_gate_up", "w_down", "rms_attn", "rms_mlp",
+                                          "key_cache", "value_cache")]
+
+
+class LlamaModel(C.Structure):
+    """struct atoma_llama_model"""
+
+    _fields_ = ([(n, C.c_int64) for n in ("hidden", "inter", "num_layers", "num_heads", "num_kv_heads", "head_dim",
+                                           "vocab", "block_size", "block_stride", "rot_stride")] +
+                [("rms_eps", C.c_float), ("softmax_scale", C.c_float), ("dtype", C.c_uint32),
+                 ("embed", C.c_void_p), ("norm_f", C.c_void_p), ("lm_head", C.c_void_p),
+                 ("cos", C.c_void_p), ("sin", C.c_void_p), ("layers", C.POINTER(LlamaLayer)),
+                 ("tp_rank", C.c_int32), ("tp_world", C.c_int32), ("p2p_regions", C.POINTER(C.c_void_p)),
+                 ("p2p_slot_bytes", C.c_int64)])
+
+
+class DecodeBatch(C.Structure):
+    """struct atoma_decode_batch"""
+
+    _fields_ = [("num_tokens", C.c_int64), ("tokens", C.c_void_p), ("hidden_in", C.c_void_p),
+                ("positions", C.c_void_p), ("slot_mapping", C.c_void_p), ("block_tables", C.c_void_p),
+                ("sequence_lengths", C.c_void_p), ("max_blocks", C.c_int64), ("scratch", C.c_void_p),
+                ("scratch_bytes", C.c_int64), ("hidden_out", C.c_void_p), ("logits", C.c_void_p),
+                ("logits_f32", C.c_void_p), ("next_tokens", C.c_void_p), ("next_logits", C.c_void_p)]
+
+
 # Exact C parameter lists, in header order.
 _RUN_MHA_ARGS = [
     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,  # q k v o lse alibi
@@ -175,6 +204,24 @@ SIGNATURES = {
     "atoma_launch_count": (C.c_int64, []),
     "atoma_reset_launch_count": (None, []),
     "atoma_version": (C.c_char_p, []),
+    # atoma_llama.h
+    "atoma_gemm_tn": (None, [C.c_void_p] * 3 + [C.c_int64] * 6 + [C.c_uint32, C.c_void_p]),
+    "atoma_qkv_rope_cache": (None, [C.c_void_p] * 3 + [C.c_int64] * 8 + [C.c_void_p] * 3 + [C.c_int64] +
+                             [C.c_void_p] * 3 + [C.c_int64] * 2 + [C.c_uint32, C.c_void_p]),
+    "atoma_gate_up_silu": (None, [C.c_void_p] * 3 + [C.c_int64] * 6 + [C.c_uint32, C.c_void_p]),
+    "atoma_add_rmsnorm": (None, [C.c_void_p] * 5 + [C.c_int64] * 6 + [C.c_float, C.c_uint32, C.c_void_p]),
+    "atoma_embedding": (None, [C.c_void_p] * 3 + [C.c_int64] * 5 + [C.c_uint32, C.c_void_p]),
+    "atoma_sample_greedy": (None, [C.c_void_p] + [C.c_int64] * 3 + [C.c_uint32] + [C.c_void_p] * 3 +
+                            [C.c_int64, C.c_void_p]),
+    "atoma_gemm_tn_push": (None, [C.c_void_p] * 2 + [C.c_int64] * 5 + [C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                                                       C.c_int64, C.c_uint32, C.c_void_p]),
+    "atoma_allreduce_recv_add_rmsnorm": (None, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 4 +
+                                         [C.c_int64] * 5 + [C.c_float, C.c_uint32, C.c_void_p]),
+    "atoma_llama_decode_scratch_bytes": (C.c_int64, [C.POINTER(LlamaModel), C.c_int64]),
+    "atoma_llama_decode_step": (None, [C.POINTER(LlamaModel), C.POINTER(DecodeBatch), C.c_void_p]),
+    "atoma_debug_skinny_trace": (None, [C.c_void_p]),
+    "atoma_debug_skinny_tuning": (None, [C.c_int] * 3),
+    "atoma_debug_skinny_mode": (None, [C.c_int] * 2),
     # atoma_ops.h
     "atoma_flash_attn_plan": (C.c_char_p, [C.POINTER(Tensor)] * 4 + [C.c_float, C.c_int64, C.c_int64, C.c_float,
                                                                     C.c_int, C.POINTER(MhaPlan)]),

@@ -269,8 +269,9 @@ rope_reshape_and_cache_kernel(T *__restrict__ q, T *__restrict__ k, const T *__r
             for (int e = 0; e < 8; ++e) {
                 const float f1 = static_cast<float>(x1[e]), f2 = static_cast<float>(x2[e]);
                 const float fc = static_cast<float>(cc[e]), fs = static_cast<float>(ss[e]);
-                y1[e] = static_cast<T>(f1 * fc - f2 * fs);
-                y2[e] = static_cast<T>(f1 * fs + f2 * fc);
+                // explicit contraction: the same bits as the fused GEMM epilogue (gemm_skinny.cu, kEpiRope)
+                y1[e] = static_cast<T>(__fmaf_rn(f1, fc, -__fmul_rn(f2, fs)));
+                y2[e] = static_cast<T>(__fmaf_rn(f1, fs, __fmul_rn(f2, fc)));
             }
             *reinterpret_cast<uint4 *>(x) = o1;
             *reinterpret_cast<uint4 *>(x + half) = o2;

@@ -42,7 +42,7 @@ const DeviceInfo &current_device_info();
 // Library-owned scratch, one per (device, stream, tag); grows monotonically, zero-initialised
 // when (re)allocated.  Used for the decode kernel's split partials + arrival counters and for the
 // device copy of a swap mapping.
-enum : int { kWorkspaceDecode = 0, kWorkspaceSwapMap = 1, kWorkspaceGemm = 2, kWorkspaceTags = 3 };
+enum : int { kWorkspaceDecode = 0, kWorkspaceSwapMap = 1, kWorkspaceGemm = 2, kWorkspaceGemmCounters = 3, kWorkspaceTags = 4 };
 void *get_workspace(cudaStream_t stream, size_t bytes, int tag);
 
 // Launch mode (process-wide, atoma_set_launch_mode): programmatic dependent launch between this
@@ -51,6 +51,8 @@ void *get_workspace(cudaStream_t stream, size_t bytes, int tag);
 // the older pages before its grid dependency resolves).
 enum : int { kLaunchPdl = 1, kLaunchConstWeights = 2, kLaunchStableCache = 4 };
 int launch_flags();
+void set_next_decode_stable_cache(int v);   // per-call form of kLaunchStableCache (thread-local, one-shot)
+int take_next_decode_stable_cache();
 
 #if defined(__CUDACC__)
 // Kernel launch with the programmatic-stream-serialization attribute when PDL is enabled: the
@@ -95,6 +97,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// One lane of the (converged) warp: true in exactly one thread.  Code under `if (elect_one_sync())`
+// keeps warp-uniform operands in uniform registers, which is what UTMALDG / UTCHMMA consume.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 
 // ---- mbarrier ----

@@ -866,7 +866,9 @@ int try_launch_decode_paged(const MhaParams &p, bool is_bf16, int64_t max_units_
     DecodeArgs a;
     a.p = p;
     a.hkt = hkt; a.hg = hg; a.tok = tok; a.tb = tb; a.g = G;
-    a.early = (launch_flags() & (kLaunchPdl | kLaunchStableCache)) == (kLaunchPdl | kLaunchStableCache) ? 1 : 0;
+    // early KV streaming needs PDL and the caller's promise for THIS call (or the legacy process-wide bit)
+    const int stable_call = take_next_decode_stable_cache();
+    a.early = ((launch_flags() & kLaunchPdl) && (stable_call || (launch_flags() & kLaunchStableCache))) ? 1 : 0;
     // Upper bound on units is known on the host only through seqlen_k (= pages * page size); the
     // kernel derives the real count from the device-side lengths.  Grid: one CTA per SM, but never
     // more CTAs than the upper bound of units.

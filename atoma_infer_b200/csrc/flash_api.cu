@@ -40,6 +40,19 @@ std::atomic<int> g_launch_flags{0};
 }
 int launch_flags() { return g_launch_flags.load(std::memory_order_relaxed); }
 
+// Per-call promise "the work in flight on the stream writes only final-page rows of the sequences
+// this decode call reads" (see ATOMA_CALL_STABLE_CACHE): set by the caller that knows it (the decode
+// step executor, run_mha_stream_flags), consumed by the next paged-decode launch on this thread.
+namespace {
+thread_local int t_next_stable_cache = 0;
+}
+void set_next_decode_stable_cache(int v) { t_next_stable_cache = v; }
+int take_next_decode_stable_cache() {
+    const int v = t_next_stable_cache;
+    t_next_stable_cache = 0;
+    return v;
+}
+
 void set_status(int code, const char *fmt, ...) {
     t_status = code;
     va_list ap;
@@ -108,8 +121,12 @@ void *get_workspace(cudaStream_t stream, size_t bytes, int tag) {
         return nullptr;
     }
     if (b.ptr) {
-        cudaStreamSynchronize(stream);
-        cudaFree(b.ptr);
+        // Never free a block that has been handed out: a CUDA graph captured earlier on this stream has
+        // the old pointer baked into its kernel nodes and may be replayed after this call.  The old
+        // block is retired (kept alive until process exit); workspaces grow rarely and only to the
+        // largest shape seen.
+        static std::vector<void *> retired;
+        retired.push_back(b.ptr);
         b.ptr = nullptr;
         b.size = 0;
     }

@@ -17,6 +17,7 @@
 //
 // Algorithmic bytes: 2 (N K + T K + T N); flops 2 T N K.
 #include "common.cuh"
+#include "skinny_args.h"
 
 #include <algorithm>
 #include <cstring>
@@ -639,12 +640,16 @@ bool launch_stream_gemm(const void *x, const void *w, void *y, int T, int64_t N,
     const int64_t units = static_cast<int64_t>(a.tiles) * a.kb_per_tile;
     const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min(di.sm_count, kGemmMaxCtas), units)));
 
-    const size_t counters_bytes = ((static_cast<size_t>(a.tiles) * sizeof(int) + 255) / 256) * 256;
+    // The arrival counters (zero between launches, self-resetting) live in their OWN workspace: in a
+    // shared buffer the boundary between counters and partials would move with the shape, and a launch
+    // with more tiles would find an earlier launch's fp32 partials where it expects zeroed counters.
+    const size_t counters_bytes = std::max<size_t>(64 * 1024, static_cast<size_t>(a.tiles) * sizeof(int));
     const size_t ws_bytes = static_cast<size_t>(grid) * 2 * a.t_pad * kTileN * sizeof(float);
-    char *ws = static_cast<char *>(get_workspace(stream, counters_bytes + ws_bytes, kWorkspaceGemm));
-    if (!ws) return false;
-    a.counters = reinterpret_cast<int *>(ws);
-    a.ws = reinterpret_cast<float *>(ws + counters_bytes);
+    char *cnt = static_cast<char *>(get_workspace(stream, counters_bytes, kWorkspaceGemmCounters));
+    char *ws = static_cast<char *>(get_workspace(stream, ws_bytes, kWorkspaceGemm));
+    if (!ws || !cnt) return false;
+    a.counters = reinterpret_cast<int *>(cnt);
+    a.ws = reinterpret_cast<float *>(ws);
     a.trace = static_cast<unsigned long long *>(g_gemm_trace);
     a.prefetch_w = ((launch_flags() & (kLaunchPdl | kLaunchConstWeights)) == (kLaunchPdl | kLaunchConstWeights)) ? 1 : 0;
     a.csize = 1;
@@ -709,6 +714,15 @@ bool launch_gemm_bf16_tn(const void *x, const void *w, void *y, int64_t T, int64
     if (T > (1 << 24)) {
         set_status(kErrUnsupported, "atoma_gemm_bf16_tn: T = %lld", static_cast<long long>(T));
         return false;
+    }
+    // Decode shapes go to the weight-streaming kernel without split-K (gemm_skinny.cu); atoma_debug_gemm_algo(2)
+    // keeps them on the stream-K kernel (diagnostics / A-B measurements).
+    if (g_gemm_algo != 2 && skinny_gemm_supported(T, K, ldx, ldw) && N < (1ll << 31)) {
+        SkinnyArgs a{};
+        a.epi = kEpiPlain;
+        a.y = y;
+        a.ldy = ldy;
+        return launch_skinny_gemm(a, x, w, static_cast<int>(T), K, ldx, ldw, 1, static_cast<int>(N), 1, 0, 0, true, stream);
     }
     if (!launch_stream_gemm(x, w, y, static_cast<int>(T), N, K, ldx, ldw, ldy, true, stream)) return false;
     return true;

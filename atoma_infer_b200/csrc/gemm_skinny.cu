@@ -1,0 +1,624 @@
+// Decode-time ("skinny") projection GEMM  y[T,N] = x[T,K] . w[N,K]^T  for T <= 128 on sm_100a, with the
+// fused epilogues of the decode step.  Call sites in the reference: q/k/v/o projections
+// models/src/llama.rs:269-271, 311; MLP gate/up/down :362-366; lm_head :476 — all candle `Linear` ->
+// cuBLAS there (no reference kernel to follow; bar = cuBLAS 12.9 on the same box).
+//
+// Why a second GEMM kernel next to gemm_bf16.cu (stream-K): at T <= 128 the GEMM is a pure weight
+// stream (algorithmic bytes 2 (N K + T K + T N), ~T flop/byte) and what separates a kernel from the
+// HBM roofline is latency, not bandwidth: round 1's stream-K kernel streamed W at 6.9 TB/s but lost
+// ~6.5 us per launch in its split reduction (fp32 partials through L2, fence, arrival counter,
+// last-arriver pass).  Here no tile is ever split:
+//  * the ACTIVATIONS are the M operand of tcgen05.mma (M = 64 for T <= 64 — rows >= T of the operand
+//    are whatever shared memory holds, they only reach accumulator rows nobody reads — else 128) and
+//    the WEIGHT tile is the N operand, whose width may be any multiple of 8 up to 256: the host picks
+//    the width so that the tiles fill one wave of the SMs (qkv of Llama-3.1-8B: 144 tiles of 48
+//    columns, o_proj / down_proj: 128 x 32, gate_up: 138 x 208, lm_head: 573 x 224 in 4 waves), each
+//    CTA streams the full K extent of its tile(s) and owns the finished accumulator row block;
+//  * a weight tile is `halves` (1 or 2) runs of `np` consecutive rows, `half_stride` rows apart,
+//    inside row group g (5-D tensor map {64 k, row, half, k block, group}; one TMA op moves
+//    [kbs k blocks][halves][np rows][128 B]): with halves = 2 an epilogue thread holds BOTH elements of
+//    a RoPE pair (d, d + D/2) or of a SwiGLU pair (gate_i, up_i), so RoPE + KV-cache scatter
+//    (llama.rs:218-304 + flash_attention.rs:361) and silu(gate) * up (llama.rs:364,
+//    f3) are applied to the accumulator before it is stored — no extra kernel, no extra pass;
+//  * tensor-parallel row-parallel projections (o_proj, down_proj; multi_gpu.rs:141-179) can PUSH the
+//    bf16 partial tile straight into every peer's receive buffer over NVLink from the epilogue (8-byte
+//    units carrying their own epoch flag, the protocol of allreduce_p2p.cu) — the all-reduce kernel
+//    that followed the GEMM shrinks to the receive side, which is fused with residual + RMSNorm
+//    (llama_ops.cu), SURVEY §8 f4;
+//  * warp 0 = TMA producer (W evict-first, x evict-last; under programmatic dependent launch with
+//    immutable weights the ring is filled with W before the grid dependency resolves), warp 1 =
+//    tcgen05.mma issuer (accumulators double-buffered in TMEM so a multi-wave CTA's epilogue overlaps
+//    its next tile), warps 2-5 = epilogue (tcgen05.ld, thread = token row).
+#include "common.cuh"
+#include "skinny_args.h"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace atoma {
+namespace {
+
+constexpr int kSkThreads = 256;             // warps: 0 W producer, 1 MMA, 2-5 epilogue, 6 idle, 7 x producer
+constexpr int kSkMaxStages = 12;
+constexpr int kSkSmemBudget = 200 * 1024;   // ring; + tail slack + 1 KiB alignment < 227 KiB
+// One thread issues only ~5 TMA tensor ops per microsecond whatever their size (measured: round 1's
+// tma_probe; here 0.25 us per stage with two ops per stage from one thread), so a stage is made of FEW,
+// LARGE ops — up to 96 KiB per stage, the weight box split over two issuing warps, x from a third.
+constexpr int kSkStageTarget = 96 * 1024;
+
+__device__ __forceinline__ unsigned long long sk_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+    return t;
+}
+
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
+                                            int c2, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+        : "memory");
+}
+
+// 32 lanes x 8 consecutive 32-bit TMEM columns -> 8 registers per thread.
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+__device__ __forceinline__ void st_relaxed_sys_v4(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
+}
+
+// fp32 accumulator -> the io type and back: every fused epilogue starts from the value the unfused
+// path would have stored (the reference materialises each projection in the model dtype).
+template <typename T>
+__device__ __forceinline__ float round_io(float f);
+template <>
+__device__ __forceinline__ float round_io<__nv_bfloat16>(float f) {
+    return __bfloat162float(__float2bfloat16_rn(f));
+}
+template <>
+__device__ __forceinline__ float round_io<__half>(float f) {
+    return __half2float(__float2half_rn(f));
+}
+template <typename T>
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 o;
+    o.x = pack2<T>(f[0], f[1]);
+    o.y = pack2<T>(f[2], f[3]);
+    o.z = pack2<T>(f[4], f[5]);
+    o.w = pack2<T>(f[6], f[7]);
+    return o;
+}
+template <typename T>
+__device__ __forceinline__ void unpack8(const uint4 &v, float (&f)[8]) {
+    const T *p = reinterpret_cast<const T *>(&v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = static_cast<float>(p[i]);
+}
+
+// Store 8 consecutive output elements of one row, `valid` of them inside the matrix.
+template <typename T>
+__device__ __forceinline__ void store8(T *dst, const uint4 &v, int valid, bool vec_ok) {
+    if (valid >= 8 && vec_ok) {
+        *reinterpret_cast<uint4 *>(dst) = v;
+    } else {
+        const T *p = reinterpret_cast<const T *>(&v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < valid) dst[i] = p[i];
+    }
+}
+
+template <typename T, int M, int EPI>
+__global__ void __launch_bounds__(kSkThreads, 1)
+gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+                   const SkinnyArgs a) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *ring = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    __shared__ __align__(8) uint64_t full[kSkMaxStages], empty[kSkMaxStages], tfull[2], tempty[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned long long t_start = a.trace ? sk_timer_ns() : 0ull;
+
+    if (tid == 0) {
+        for (int i = 0; i < a.stages; ++i) {
+            mbar_init(&full[i], 2);   // one arrive.expect_tx from the W producer, one from the x producer
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 4);   // one arrival per epilogue warp
+        }
+        fence_mbar_init();
+        tma_prefetch_desc(&map_w);
+        tma_prefetch_desc(&map_x);
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, a.tmem_cols);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    const int my_tiles = (a.tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int total = my_tiles * a.chunks;   // (tile, k chunk) stages this CTA streams
+
+    // The producer and MMA warps run their loops CONVERGED, all 32 lanes, on warp-uniform values; only the
+    // asynchronous instructions themselves sit under elect.sync.  (Inside an `if (lane == 0)` region the
+    // compiler keeps every operand in vector registers and wraps each UTMALDG / UTCHMMA — which take uniform
+    // registers — in an R2UR + ELECT waterfall loop: ~70 cycles per tcgen05.mma and ~0.2 us per TMA op,
+    // measured; that, not HBM, bounded the first version of this kernel.)
+    if (warp == 0 || warp == 7) {
+        // ============================ TMA producers ============================
+        // warp 0: the weight op(s) of every stage; warp 7: the x op.  Each arrives on the stage's full
+        // barrier with its own byte count.
+        const bool is_w = warp == 0;
+        if (is_w) pdl_launch_dependents();
+        const int w_op_bytes = a.w_bytes / a.w_ops;
+        // Under programmatic dependent launch with immutable weights the ring is filled with W while the
+        // previous kernel drains; x (its output) only after the grid dependency has resolved.
+        const int pre = (is_w && a.prefetch_w) ? min(a.stages, total) : 0;
+        if (pre == 0) pdl_wait();
+        int stage = 0;
+        uint32_t phase = 0;
+        int n = 0;
+        // no integer division inside the stage loop (a runtime division costs this warp hundreds of
+        // cycles — more than a whole stage of MMAs)
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int g = tile / a.tiles_per_group, p0 = (tile - g * a.tiles_per_group) * a.np;
+            for (int ch = 0; ch < a.chunks; ++ch, ++n) {
+                if (n == pre && pre != 0) {
+                    pdl_wait();
+                    if (a.trace && lane == 0) a.trace[blockIdx.x * 4 + 0] = t_start;
+                }
+                mbar_wait(&empty[stage], phase ^ 1);   // passes at once during the first trip round the ring
+                unsigned char *dst = ring + stage * a.stage_bytes;
+                if (elect_one_sync()) {
+                    // W is read exactly once by exactly one CTA: evict-first.  x is re-read by every CTA: keep it.
+                    if (is_w) {
+                        if (a.debug_skip & 2) {
+                            mbar_arrive(&full[stage]);
+                        } else {
+                            mbar_arrive_expect_tx(&full[stage], a.w_bytes);
+                            for (int o = 0; o < a.w_ops; ++o)
+                                tma_load_5d(dst + o * w_op_bytes, &map_w, &full[stage], 0, p0, 0, ch * a.kbs + o * a.wkb, g,
+                                            kL2EvictFirst);
+                        }
+                    } else {
+                        if (a.debug_skip & 1) {
+                            mbar_arrive(&full[stage]);
+                        } else {
+                            mbar_arrive_expect_tx(&full[stage], a.x_bytes);
+                            tma_load_3d(dst + a.w_bytes, &map_x, &full[stage], 0, 0, ch * a.kbs, kL2EvictLast);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (++stage == a.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+        if (pre != 0 && n <= pre) pdl_wait();   // everything fitted in the prefetch: still order after the predecessor
+        if (a.trace && pre == 0 && is_w && lane == 0) a.trace[blockIdx.x * 4 + 0] = t_start;
+    } else if (warp == 1) {
+        // ============================ MMA issuer ============================
+        pdl_wait();
+        const uint32_t idesc = umma_idesc_f16(M, a.n_tile, a.is_bf16 != 0);
+        const int w_slab = a.n_tile * 128, x_slab = a.t_box * 128;
+        const uint32_t ring_u32 = smem_u32(ring);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int buf = it & 1;
+            mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);   // the epilogue drained this accumulator
+            tc_fence_after_sync();
+            // `nacc` accumulators per tile, used round-robin (diagnostics; 1 by default)
+            const uint32_t tmem_d0 = tmem_base + buf * (a.nacc * a.acc_stride);
+            int step = 0;
+            for (int ch = 0; ch < a.chunks; ++ch) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after_sync();
+                if (a.trace && it == 0 && ch == 0 && lane == 0) a.trace[blockIdx.x * 4 + 1] = sk_timer_ns();
+                const uint32_t base = ring_u32 + stage * a.stage_bytes;
+                const int nkb = min(a.kbs, a.kb_total - ch * a.kbs);   // k blocks past K are zero-filled: skip
+                if (elect_one_sync()) {
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        const uint64_t da = umma_desc_k_sw128(base + a.w_bytes + kb * x_slab);
+                        const uint64_t db = umma_desc_k_sw128(base + kb * w_slab);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {   // 16 elements = 32 bytes along K inside the swizzle row: +2
+                            const int acc = (step + kb * 4 + k) & (a.nacc - 1);
+                            umma_f16_ss(tmem_d0 + acc * a.acc_stride, da + 2 * k, db + 2 * k, idesc,
+                                        (step + kb * 4 + k) >= a.nacc ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&empty[stage]);   // the slot is free once these MMAs have read it
+                }
+                __syncwarp();
+                step += nkb * 4;
+                if (++stage == a.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            if (elect_one_sync()) umma_commit(&tfull[buf]);
+            __syncwarp();
+        }
+    } else if (warp >= 2 && warp <= 5) {
+        // ============================ epilogue warps (2..5) ============================
+        pdl_wait();
+        const int quad = warp & 3;   // the TMEM lane quadrant this warp may read
+        // M = 64: accumulator row r lives in lane (r % 16) + 32 (r / 16); M = 128: row r in lane r.
+        const int row = (M == 64) ? quad * 16 + lane : quad * 32 + lane;
+        const bool row_ok = (M == 64 ? lane < 16 : true) && row < a.T;
+        T *y = static_cast<T *>(a.y) + static_cast<int64_t>(row_ok ? row : 0) * a.ldy;
+        const bool y_vec = (a.ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0);
+        const int J = a.J, np = a.np;
+
+        // per-row constants of the fused epilogues
+        const T *cos_r = nullptr, *sin_r = nullptr;
+        int64_t cache_row = -1;
+        if (EPI == kEpiRope && row_ok) {
+            const int64_t pos = a.positions[row];
+            cos_r = static_cast<const T *>(a.cos) + pos * a.rot_stride;
+            sin_r = static_cast<const T *>(a.sin) + pos * a.rot_stride;
+            const int64_t slot = a.slot_mapping ? a.slot_mapping[row] : -1;   // < 0: padded token (cache_manager.cu:151-155)
+            if (slot >= 0 && a.k_cache)
+                cache_row = (slot / a.block_size) * a.block_stride + (slot % a.block_size) * a.num_kv_heads * (2 * J);
+        }
+        uint32_t epoch = 0;
+        int slot_sel = 0;
+        if (EPI == kEpiPush) {
+            epoch = a.push_state[0] + 1;   // this all-reduce's epoch (advanced by the receive-side kernel)
+            slot_sel = static_cast<int>(epoch & 1u);
+        }
+
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int buf = it & 1;
+            const int g = tile / a.tiles_per_group, p0 = (tile % a.tiles_per_group) * np;
+            mbar_wait(&tfull[buf], (it >> 1) & 1);
+            tc_fence_after_sync();
+            if (a.trace && tid == 64) a.trace[blockIdx.x * 4 + 2] = sk_timer_ns();
+            const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * (a.nacc * a.acc_stride);
+            // 8 consecutive columns of the tile: the sum of the nacc partial accumulators (fixed order)
+            auto load8 = [&](int col, uint32_t (&v)[8]) {
+                tmem_ld_32x32b_x8(tacc + col, v);
+                for (int i = 1; i < a.nacc; ++i) {
+                    uint32_t w[8];
+                    tmem_ld_32x32b_x8(tacc + i * a.acc_stride + col, w);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+                }
+            };
+
+            if (EPI == kEpiPlain || EPI == kEpiPush) {
+                // columns [p0, p0 + np) of the output, 8 at a time, two TMEM loads in flight
+                for (int c = 0; c < np; c += 16) {
+                    uint32_t v0[8], v1[8];
+                    load8(c, v0);
+                    if (c + 8 < np) load8(c + 8, v1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int j0 = p0 + c + 8 * u;
+                        if (c + 8 * u >= np || j0 >= J || !row_ok) continue;
+                        float f[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(u == 0 ? v0[i] : v1[i]);
+                        const uint4 o = pack8<T>(f);
+                        if (EPI == kEpiPlain) {
+                            store8<T>(y + j0, o, J - j0, y_vec);
+                        } else {
+                            // tensor parallel: this rank's addend of vector i goes to recv[slot][rank] of EVERY
+                            // rank (own included) as two 16-byte stores {w0,e,w1,e} {w2,e,w3,e}
+                            const int64_t i16 = (static_cast<int64_t>(row) * J + j0) >> 3;
+                            const int64_t off = a.push_recv_offset + slot_sel * a.push_slot_stride +
+                                                a.push_rank * a.push_recv_stride + i16 * 16;
+#pragma unroll 1
+                            for (int d = 0; d < a.push_world; ++d) {
+                                const int r = (a.push_rank + d) % a.push_world;
+                                unsigned char *dst = a.push_region[r] + off;
+                                st_relaxed_sys_v4(dst, o.x, epoch, o.y, epoch);
+                                st_relaxed_sys_v4(dst + a.push_plane_bytes, o.z, epoch, o.w, epoch);
+                            }
+                        }
+                    }
+                }
+            } else {
+                // paired tile: accumulator columns [0, np) = first half (rows p0.. of the group), [np, 2 np) =
+                // second half (the same rows `half_stride` further down)
+                const bool is_q = g < a.num_heads, is_k = !is_q && g < a.num_heads + a.num_kv_heads;
+                for (int c = 0; c < np; c += 8) {
+                    uint32_t lo[8], hi[8];
+                    load8(c, lo);
+                    load8(np + c, hi);
+                    tmem_ld_wait();
+                    const int j0 = p0 + c;
+                    if (j0 >= J || !row_ok) continue;
+                    float f1[8], f2[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        f1[i] = round_io<T>(__uint_as_float(lo[i]));
+                        f2[i] = round_io<T>(__uint_as_float(hi[i]));
+                    }
+                    if (EPI == kEpiSilu) {
+                        // silu(gate) * up (llama.rs:364): fp32 on the model-dtype projections, one rounding
+                        float o[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o[i] = (f1[i] / (1.f + __expf(-f1[i]))) * f2[i];
+                        store8<T>(y + j0, pack8<T>(o), J - j0, y_vec);
+                    } else {
+                        // RoPE (non-interleaved, candle_nn::rotary_emb::rope; llama.rs:218-251) on q and k heads;
+                        // v heads pass through.  Same arithmetic as rope_reshape_and_cache_kernel.
+                        float o1[8], o2[8];
+                        if (is_q || is_k) {
+                            float fc[8], fs[8];
+                            unpack8<T>(*reinterpret_cast<const uint4 *>(cos_r + j0), fc);
+                            unpack8<T>(*reinterpret_cast<const uint4 *>(sin_r + j0), fs);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                o1[i] = __fmaf_rn(f1[i], fc[i], -__fmul_rn(f2[i], fs[i]));
+                                o2[i] = __fmaf_rn(f1[i], fs[i], __fmul_rn(f2[i], fc[i]));
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                o1[i] = f1[i];
+                                o2[i] = f2[i];
+                            }
+                        }
+                        const uint4 w1 = pack8<T>(o1), w2 = pack8<T>(o2);
+                        T *dst = y + static_cast<int64_t>(g) * (2 * J) + j0;
+                        store8<T>(dst, w1, J - j0, y_vec);
+                        store8<T>(dst + J, w2, J - j0, y_vec);
+                        if (!is_q && cache_row >= 0) {
+                            // reshape_and_cache_flash (cache_manager.cu:140-170): k_cache[slot / bs, slot % bs, head, :]
+                            T *cache = static_cast<T *>(is_k ? a.k_cache : a.v_cache);
+                            const int kvh = g - a.num_heads - (is_k ? 0 : a.num_kv_heads);
+                            T *cd = cache + cache_row + static_cast<int64_t>(kvh) * (2 * J) + j0;
+                            store8<T>(cd, w1, J - j0, true);
+                            store8<T>(cd + J, w2, J - j0, true);
+                        }
+                    }
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (a.trace && tid == 0) a.trace[blockIdx.x * 4 + 3] = sk_timer_ns();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, a.tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct MapKey {
+    const void *ptr;
+    uint64_t dims[5], strides[4];
+    uint32_t box[5];
+    int rank, bf16;
+    bool operator==(const MapKey &o) const { return std::memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapEntry {
+    MapKey key;
+    CUtensorMap map;
+};
+
+// N-D tiled tensor map of 16-bit elements, 128-byte swizzle, innermost box = 64 elements.
+bool make_tiled_map(CUtensorMap *out, const void *ptr, int rank, const uint64_t *dims, const uint64_t *strides,
+                    const uint32_t *box, bool is_bf16) {
+    static thread_local std::vector<MapEntry> cache;
+    MapKey key;
+    std::memset(&key, 0, sizeof(key));
+    key.ptr = ptr;
+    key.rank = rank;
+    key.bf16 = is_bf16;
+    for (int i = 0; i < rank; ++i) {
+        key.dims[i] = dims[i];
+        key.box[i] = box[i];
+        if (i + 1 < rank) key.strides[i] = strides[i];
+    }
+    for (const MapEntry &e : cache)
+        if (e.key == key) {
+            *out = e.map;
+            return true;
+        }
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return false;
+    cuuint64_t d[5], s[4];
+    cuuint32_t b[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        d[i] = dims[i];
+        b[i] = box[i];
+        es[i] = 1;
+        if (i + 1 < rank) s[i] = strides[i];
+    }
+    CUresult r = enc(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                     static_cast<cuuint32_t>(rank), const_cast<void *>(ptr), d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_status(kErrDriver, "skinny gemm: cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
+        return false;
+    }
+    if (cache.size() >= 1024) cache.clear();
+    cache.push_back(MapEntry{key, *out});
+    return true;
+}
+
+void *g_sk_trace = nullptr;
+int g_sk_force_np = 0;       // diagnostics: override the tile width (rows per half)
+int g_sk_force_kbs = 0;      // diagnostics: override the k blocks per stage
+int g_sk_stage_limit = 0;
+int g_sk_debug_skip = 0;     // diagnostics (timing experiments only; results are garbage): 1 = no x loads, 2 = no W loads
+int g_sk_w_ops = 1;          // weight ops per stage (1 | 2)
+int g_sk_nacc = 0;           // diagnostics: cap on the independent accumulators per tile (0 = automatic)
+
+// Rows per half per tile (multiple of 8, np * halves <= 256) minimising waves x (tile width + a fixed
+// per-tile cost); ties go to the wider tile (fewer CTAs, fewer x re-reads).
+int choose_np(int G, int J, int halves, int sms) {
+    int best = 8;
+    long best_cost = -1;
+    const int np_max = std::min(256 / halves, (J + 7) / 8 * 8);
+    for (int np = 8; np <= np_max; np += 8) {
+        const long tiles = static_cast<long>(G) * ((J + np - 1) / np);
+        const long waves = (tiles + sms - 1) / sms;
+        const long cost = waves * (static_cast<long>(np) * halves + 8);
+        if (best_cost < 0 || cost <= best_cost) {
+            best = np;
+            best_cost = cost;
+        }
+    }
+    return best;
+}
+
+template <typename T, int M>
+cudaError_t launch_epi(int epi, dim3 grid, size_t smem, cudaStream_t stream, const CUtensorMap &mw, const CUtensorMap &mx,
+                       const SkinnyArgs &a) {
+    static thread_local int attr_dev = -1;
+    const DeviceInfo &di = current_device_info();
+    if (attr_dev != di.ordinal) {
+        const int lim = kSkSmemBudget + 128 * 128 + 1024;
+        cudaError_t e = cudaSuccess;
+        auto set = [&](auto *k) {
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        };
+        set(gemm_skinny_kernel<T, M, kEpiPlain>);
+        set(gemm_skinny_kernel<T, M, kEpiRope>);
+        set(gemm_skinny_kernel<T, M, kEpiSilu>);
+        set(gemm_skinny_kernel<T, M, kEpiPush>);
+        if (e != cudaSuccess) return e;
+        attr_dev = di.ordinal;
+    }
+    switch (epi) {
+        case kEpiPlain: return launch_ex(gemm_skinny_kernel<T, M, kEpiPlain>, grid, dim3(kSkThreads), smem, stream, mw, mx, a);
+        case kEpiRope: return launch_ex(gemm_skinny_kernel<T, M, kEpiRope>, grid, dim3(kSkThreads), smem, stream, mw, mx, a);
+        case kEpiSilu: return launch_ex(gemm_skinny_kernel<T, M, kEpiSilu>, grid, dim3(kSkThreads), smem, stream, mw, mx, a);
+        case kEpiPush: return launch_ex(gemm_skinny_kernel<T, M, kEpiPush>, grid, dim3(kSkThreads), smem, stream, mw, mx, a);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace
+
+void set_skinny_trace(void *device_buf) { g_sk_trace = device_buf; }
+void set_skinny_tuning(int np, int kbs, int stages) {
+    g_sk_force_np = np;
+    g_sk_force_kbs = kbs;
+    g_sk_stage_limit = stages;
+}
+void set_skinny_debug(int skip, int w_ops) {
+    g_sk_debug_skip = skip & 3;
+    g_sk_nacc = (skip >> 4) & 7;          // bits 4-6: accumulator cap (1, 2, 4; 0 = automatic)
+    g_sk_w_ops = w_ops == 2 ? 2 : 1;
+}
+
+bool skinny_gemm_supported(int64_t T, int64_t K, int64_t ldx, int64_t ldw) {
+    return T >= 1 && T <= 128 && K >= 64 && K % 64 == 0 && ldx % 8 == 0 && ldw % 8 == 0 &&
+           current_device_info().cc_major == 10;
+}
+
+// Launch one skinny GEMM.  `a` arrives with the epilogue fields filled in; this fills the tiling.
+//   w: G groups x halves x J rows (row stride ldw; halves `half_stride_rows` apart, groups
+//   `group_stride_rows` apart), x [T, K] row stride ldx.
+bool launch_skinny_gemm(SkinnyArgs a, const void *x, const void *w, int T, int64_t K, int64_t ldx, int64_t ldw, int G,
+                        int J, int halves, int64_t half_stride_rows, int64_t group_stride_rows, bool is_bf16,
+                        cudaStream_t stream) {
+    const DeviceInfo &di = current_device_info();
+    a.T = T;
+    a.m = T <= 64 ? 64 : 128;
+    a.t_box = (T + 7) / 8 * 8;
+    a.kb_total = static_cast<int>(K / 64);
+    a.J = J;
+    a.G = G;
+    a.halves = halves;
+    a.np = g_sk_force_np > 0 ? g_sk_force_np : choose_np(G, J, halves, di.sm_count);
+    a.n_tile = a.np * halves;
+    a.tiles_per_group = (J + a.np - 1) / a.np;
+    a.tiles = G * a.tiles_per_group;
+    const int per_kb = (a.n_tile + a.t_box) * 128;
+    int kbs = 16;
+    while (kbs > 1 && (kbs * per_kb > kSkStageTarget || kbs > a.kb_total)) kbs >>= 1;
+    if (g_sk_force_kbs > 0) kbs = g_sk_force_kbs;
+    a.kbs = kbs;
+    a.w_ops = (kbs >= 2 && g_sk_w_ops == 2) ? 2 : 1;   // the weight box of a stage is issued as one or two ops
+    a.debug_skip = g_sk_debug_skip;
+    a.wkb = kbs / a.w_ops;
+    a.chunks = (a.kb_total + kbs - 1) / kbs;
+    a.w_bytes = kbs * a.n_tile * 128;
+    a.x_bytes = kbs * a.t_box * 128;
+    a.stage_bytes = a.w_bytes + a.x_bytes;
+    a.stages = std::min(kSkMaxStages, kSkSmemBudget / a.stage_bytes);
+    if (g_sk_stage_limit > 0) a.stages = std::min(a.stages, g_sk_stage_limit);
+    if (a.stages < 2) {
+        set_status(kErrUnsupported, "skinny gemm: stage of %d bytes does not fit", a.stage_bytes);
+        return false;
+    }
+    a.acc_stride = (a.n_tile + 31) / 32 * 32;
+    // independent accumulation chains (diagnostics only: measured, they do not help — the cost was the
+    // issuing thread's instruction stream, not the tensor pipe)
+    a.nacc = 1;
+    if (g_sk_nacc > 1) a.nacc = std::min(g_sk_nacc, a.acc_stride <= 64 ? 4 : (a.acc_stride <= 128 ? 2 : 1));
+    int cols = 32;
+    while (cols < 2 * a.nacc * a.acc_stride) cols <<= 1;
+    a.tmem_cols = cols;
+    a.is_bf16 = is_bf16 ? 1 : 0;
+    a.prefetch_w = ((launch_flags() & (kLaunchPdl | kLaunchConstWeights)) == (kLaunchPdl | kLaunchConstWeights)) ? 1 : 0;
+    a.trace = static_cast<unsigned long long *>(g_sk_trace);
+
+    CUtensorMap mw, mx;
+    {
+        const uint64_t dims[5] = {64, static_cast<uint64_t>(J), static_cast<uint64_t>(halves),
+                                  static_cast<uint64_t>(a.kb_total), static_cast<uint64_t>(G)};
+        const uint64_t strides[4] = {static_cast<uint64_t>(ldw) * 2, static_cast<uint64_t>(half_stride_rows) * ldw * 2, 128,
+                                     static_cast<uint64_t>(group_stride_rows) * ldw * 2};
+        // sizes of 1 keep their (unused) stride legal: any multiple of 16
+        uint64_t st[4] = {strides[0], halves > 1 ? strides[1] : strides[0], 128, G > 1 ? strides[3] : strides[0]};
+        const uint32_t box[5] = {64, static_cast<uint32_t>(a.np), static_cast<uint32_t>(halves), static_cast<uint32_t>(a.wkb), 1};
+        if (!make_tiled_map(&mw, w, 5, dims, st, box, is_bf16)) return false;
+    }
+    {
+        const uint64_t dims[3] = {64, static_cast<uint64_t>(T), static_cast<uint64_t>(a.kb_total)};
+        const uint64_t strides[2] = {static_cast<uint64_t>(ldx) * 2, 128};
+        const uint32_t box[3] = {64, static_cast<uint32_t>(a.t_box), static_cast<uint32_t>(kbs)};
+        if (!make_tiled_map(&mx, x, 3, dims, strides, box, is_bf16)) return false;
+    }
+    const int grid = std::min(a.tiles, di.sm_count);
+    // ring + the rows an M-row A descriptor reads past the last x slab + alignment slack
+    const size_t smem = static_cast<size_t>(a.stages) * a.stage_bytes + a.m * 128 + 1024;
+    cudaError_t e;
+    if (is_bf16) {
+        e = a.m == 64 ? launch_epi<__nv_bfloat16, 64>(a.epi, dim3(grid), smem, stream, mw, mx, a)
+                      : launch_epi<__nv_bfloat16, 128>(a.epi, dim3(grid), smem, stream, mw, mx, a);
+    } else {
+        e = a.m == 64 ? launch_epi<__half, 64>(a.epi, dim3(grid), smem, stream, mw, mx, a)
+                      : launch_epi<__half, 128>(a.epi, dim3(grid), smem, stream, mw, mx, a);
+    }
+    note_launch();
+    if (e != cudaSuccess) {
+        set_status(static_cast<int>(e), "gemm_skinny_kernel: %s", cudaGetErrorString(e));
+        return false;
+    }
+    return check_launch("gemm_skinny_kernel");
+}
+
+}  // namespace atoma

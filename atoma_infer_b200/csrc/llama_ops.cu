@@ -1,0 +1,405 @@
+// The small kernels of a Llama decode step around the projections: token
+// embedding gather, residual add + RMSNorm (plain, and as the receive side of the tensor-parallel
+// all-reduce whose send side is the o_proj / down_proj GEMM epilogue, row f4), and greedy sampling
+// of the lm_head logits on the device.
+//
+// Reference behaviour restated (third-party arithmetic: candle-nn / candle-kernels 0.9.2-alpha.1 are
+// registry dependencies, not under /root/reference — parity for these ops is unpinned there; the
+// call sites are what is followed):
+//   * models/src/llama.rs:398-410  Block::forward:  x = attn(rms_1(x)) + residual;  x = mlp(rms_2(x)) + residual
+//     — the adds are in the model dtype (bf16), RMSNorm computes in fp32 on the bf16 input:
+//     y = bf16( x * rsqrt(mean(x^2) + eps) * w ).
+//   * models/src/llama.rs:456-478  Llama::forward: wte gather, blocks, ln_f, index_select of the selected
+//     token rows, lm_head, logits.to_dtype(F32).
+//   * backends/vllm/src/model_executor.rs:227-262: per sequence, copy the full-vocab logits row to the
+//     host (to_vec1) and sample there; greedy = candle_transformers LogitsProcessor::sample_argmax =
+//     `iter().enumerate().max_by(total_cmp)`, i.e. the LAST index among equal maxima; the reported
+//     "logprob" is the raw logit of the sampled token.  Here: one kernel, 8 bytes per sequence leave
+//     the device instead of vocab * 4.
+//   * models/src/multi_gpu.rs:141-179 AllReduce::cuda_fwd: ncclAllReduce(sum) of the [T, hidden] bf16
+//     partial projection; result in bf16.
+#include "common.cuh"
+
+#include "atoma_flash.h"
+
+#include <algorithm>
+
+namespace atoma {
+namespace {
+
+constexpr int kNormMaxVec = 4;   // 16-byte vectors per thread: hidden <= 8 * 512 * 4
+
+template <typename T>
+__device__ __forceinline__ void unpack8f(const uint4 &v, float (&f)[8]) {
+    const T *p = reinterpret_cast<const T *>(&v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = static_cast<float>(p[i]);
+}
+template <typename T>
+__device__ __forceinline__ uint4 pack8f(const float (&f)[8]) {
+    uint4 o;
+    o.x = pack2<T>(f[0], f[1]);
+    o.y = pack2<T>(f[2], f[3]);
+    o.z = pack2<T>(f[4], f[5]);
+    o.w = pack2<T>(f[6], f[7]);
+    return o;
+}
+template <typename T>
+__device__ __forceinline__ float round_to(float f) {
+    return static_cast<float>(static_cast<T>(f));
+}
+
+__device__ __forceinline__ float block_sum(float v, float *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float s = 0.f;
+    for (int i = 0; i < nw; ++i) s += red[i];   // fixed order: every thread gets the same bits
+    return s;
+}
+
+__device__ __forceinline__ uint4 ld_volatile_v4(const void *p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ops_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+    return t;
+}
+
+struct NormArgs {
+    const void *x;         // [T, hidden] addend (projection output) or null
+    const void *residual;  // [T, hidden] or null (first layer: h = x)
+    void *residual_out;    // [T, hidden] h = x + residual (may alias residual or x), or null
+    const void *weight;    // [hidden]
+    void *normed;          // [T, hidden] rmsnorm(h) * weight, or null (only the add is wanted)
+    int64_t ldx, ldr, ldro, ldn;
+    int hidden, T;
+    float eps;
+    // receive side of the tensor-parallel all-reduce (world > 1): x is the rank-order fp32 sum of the
+    // addends every rank pushed into recv[slot][r] of this rank's region, rounded to the io type
+    unsigned char *region;   // local region
+    int64_t recv_offset, slot_stride, recv_stride, plane_bytes;
+    int world;
+    unsigned long long timeout_ns;
+};
+
+// One CTA per token row; thread t owns the 16-byte vectors t, t + blockDim, ...
+template <typename T, int W>
+__global__ void __launch_bounds__(512) add_rmsnorm_kernel(const NormArgs a) {
+    __shared__ float red[32];
+    __shared__ uint32_t s_state[2];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = blockIdx.x, nvec = a.hidden / 8;
+    uint32_t *state = reinterpret_cast<uint32_t *>(a.region);
+    uint32_t e = 0;
+    bool failed = false;
+    if (W > 1) {
+        if (threadIdx.x == 0) {
+            s_state[0] = *reinterpret_cast<volatile uint32_t *>(&state[0]);
+            s_state[1] = *reinterpret_cast<volatile uint32_t *>(&state[2]);
+        }
+        __syncthreads();
+        e = s_state[0] + 1;               // this all-reduce's epoch
+        if (s_state[1] != 0) return;      // a peer failed to arrive earlier: do not wait for it again (block-uniform)
+    }
+    float h[kNormMaxVec][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int u = 0; u < kNormMaxVec; ++u) {
+        const int v = threadIdx.x + u * blockDim.x;
+        if (v >= nvec) break;
+        float x[8];
+        if (W > 1) {
+            // poll the W addends of vector i (8-byte units {data, epoch}); add in rank order, round once
+            const int64_t i = static_cast<int64_t>(row) * nvec + v;
+            const unsigned char *src = a.region + a.recv_offset + (e & 1u) * a.slot_stride + i * 16;
+            uint4 lo[W > 1 ? W : 1], hi[W > 1 ? W : 1];
+            bool done[W > 1 ? W : 1];
+#pragma unroll
+            for (int r = 0; r < W; ++r) done[r] = false;
+            const unsigned long long t0 = ops_timer_ns();
+            for (int spin = 0;; ++spin) {
+                bool all = true;
+#pragma unroll
+                for (int r = 0; r < W; ++r) {
+                    if (!done[r]) {
+                        lo[r] = ld_volatile_v4(src + r * a.recv_stride);
+                        hi[r] = ld_volatile_v4(src + r * a.recv_stride + a.plane_bytes);
+                        done[r] = lo[r].y == e && lo[r].w == e && hi[r].y == e && hi[r].w == e;
+                        all = all && done[r];
+                    }
+                }
+                if (all) break;
+                if ((spin & 63) == 63 && ops_timer_ns() - t0 > a.timeout_ns) {
+                    failed = true;
+                    break;
+                }
+            }
+            if (failed) break;
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+            for (int r = 0; r < W; ++r) {
+                float f[8];
+                unpack8f<T>(make_uint4(lo[r].x, lo[r].z, hi[r].x, hi[r].z), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = round_to<T>(acc[j]);   // the all-reduce result is in the io type
+        } else if (a.x) {
+            unpack8f<T>(*reinterpret_cast<const uint4 *>(static_cast<const T *>(a.x) + static_cast<int64_t>(row) * a.ldx + v * 8), x);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = 0.f;
+        }
+        if (a.residual) {
+            float r[8];
+            unpack8f<T>(*reinterpret_cast<const uint4 *>(static_cast<const T *>(a.residual) + static_cast<int64_t>(row) * a.ldr + v * 8), r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = round_to<T>(x[j] + r[j]);   // the add is in the model dtype
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            h[u][j] = x[j];
+            ss += x[j] * x[j];
+        }
+        if (a.residual_out)
+            *reinterpret_cast<uint4 *>(static_cast<T *>(a.residual_out) + static_cast<int64_t>(row) * a.ldro + v * 8) = pack8f<T>(x);
+    }
+    int any_failed = 0;
+    if (W > 1) {
+        any_failed = __syncthreads_or(failed ? 1 : 0);
+        if (any_failed && threadIdx.x == 0) atomicExch(&state[2], 1u);   // error word: a peer never arrived
+    }
+    const float total = block_sum(ss, red);
+    if (a.normed && !any_failed) {
+        const float scale = rsqrtf(total / static_cast<float>(a.hidden) + a.eps);
+#pragma unroll
+        for (int u = 0; u < kNormMaxVec; ++u) {
+            const int v = threadIdx.x + u * blockDim.x;
+            if (v >= nvec) break;
+            float w[8], o[8];
+            unpack8f<T>(*reinterpret_cast<const uint4 *>(static_cast<const T *>(a.weight) + v * 8), w);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = scale * h[u][j] * w[j];
+            *reinterpret_cast<uint4 *>(static_cast<T *>(a.normed) + static_cast<int64_t>(row) * a.ldn + v * 8) = pack8f<T>(o);
+        }
+    }
+    if (W > 1) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(&state[1], 1u) == gridDim.x - 1) {   // last CTA: the next all-reduce sees the next epoch
+                state[1] = 0;
+                __threadfence();
+                state[0] = e;
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) embedding_kernel(const uint32_t *__restrict__ tokens, const T *__restrict__ table,
+                                                        T *__restrict__ out, int hidden, int64_t ld_table, int64_t ldo,
+                                                        int64_t vocab) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = blockIdx.x;
+    int64_t tok = tokens[row];
+    if (tok >= vocab) tok = vocab - 1;   // candle's index_select would fail the launch; never fault here
+    const uint4 *src = reinterpret_cast<const uint4 *>(table + tok * ld_table);
+    uint4 *dst = reinterpret_cast<uint4 *>(out + static_cast<int64_t>(row) * ldo);
+    for (int v = threadIdx.x; v < hidden / 8; v += blockDim.x) dst[v] = src[v];
+}
+
+// Greedy sampling: one CTA per row; ties -> the LAST index (max_by semantics, see the header comment).
+// NaN logits: total_cmp orders +NaN above +inf; restated by comparing the sign-magnitude integer key.
+__device__ __forceinline__ int32_t total_order_key(float f) {
+    int32_t b = __float_as_int(f);
+    return b ^ ((b >> 31) & 0x7fffffff);
+}
+template <typename T>
+__global__ void __launch_bounds__(1024) argmax_kernel(const T *__restrict__ logits, int64_t ld, int vocab,
+                                                      uint32_t *__restrict__ token_out, float *__restrict__ logit_out,
+                                                      float *__restrict__ logits_f32, int64_t ld_f32) {
+    __shared__ int32_t s_key[32];
+    __shared__ int s_idx[32];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = blockIdx.x;
+    const T *x = logits + static_cast<int64_t>(row) * ld;
+    int32_t best_key = INT32_MIN;
+    int best_idx = -1;
+    const int nvec = vocab / 8;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+        float f[8];
+        unpack8f<T>(ld_nc_v4(x + v * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int32_t k = total_order_key(f[j]);
+            if (k >= best_key) {   // indices ascend within a thread: >= keeps the last maximum
+                best_key = k;
+                best_idx = v * 8 + j;
+            }
+        }
+        if (logits_f32) {
+            float4 *o = reinterpret_cast<float4 *>(logits_f32 + static_cast<int64_t>(row) * ld_f32 + v * 8);
+            o[0] = make_float4(f[0], f[1], f[2], f[3]);
+            o[1] = make_float4(f[4], f[5], f[6], f[7]);
+        }
+    }
+    for (int i = nvec * 8 + threadIdx.x; i < vocab; i += blockDim.x) {
+        const float f = static_cast<float>(x[i]);
+        const int32_t k = total_order_key(f);
+        if (k > best_key || (k == best_key && i > best_idx)) {
+            best_key = k;
+            best_idx = i;
+        }
+        if (logits_f32) logits_f32[static_cast<int64_t>(row) * ld_f32 + i] = f;
+    }
+    auto better = [](int32_t k1, int i1, int32_t k2, int i2) { return k1 > k2 || (k1 == k2 && i1 > i2); };
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int32_t k = __shfl_xor_sync(0xffffffffu, best_key, o);
+        const int i = __shfl_xor_sync(0xffffffffu, best_idx, o);
+        if (better(k, i, best_key, best_idx)) {
+            best_key = k;
+            best_idx = i;
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) {
+        s_key[warp] = best_key;
+        s_idx[warp] = best_idx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < nw; ++w)
+            if (better(s_key[w], s_idx[w], best_key, best_idx)) {
+                best_key = s_key[w];
+                best_idx = s_idx[w];
+            }
+        token_out[row] = static_cast<uint32_t>(best_idx < 0 ? 0 : best_idx);
+        if (logit_out) logit_out[row] = best_idx < 0 ? 0.f : static_cast<float>(x[best_idx]);
+    }
+}
+
+inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <typename T>
+cudaError_t launch_norm(const NormArgs &a, int threads, cudaStream_t stream) {
+    switch (a.world) {
+        case 1: return launch_ex(add_rmsnorm_kernel<T, 1>, dim3(a.T), dim3(threads), 0, stream, a);
+        case 2: return launch_ex(add_rmsnorm_kernel<T, 2>, dim3(a.T), dim3(threads), 0, stream, a);
+        case 4: return launch_ex(add_rmsnorm_kernel<T, 4>, dim3(a.T), dim3(threads), 0, stream, a);
+        case 8: return launch_ex(add_rmsnorm_kernel<T, 8>, dim3(a.T), dim3(threads), 0, stream, a);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace
+
+// p2p region geometry shared with allreduce_p2p.cu (kArHeaderBytes = 4096, two staging slots, then
+// recv[2 slots][8 source ranks][2 planes of slot bytes]).
+void p2p_layout(int64_t slot_bytes, int64_t *recv_offset, int64_t *slot_stride, int64_t *recv_stride) {
+    const int64_t s = (slot_bytes + 255) / 256 * 256;
+    *recv_stride = 2 * s;
+    *slot_stride = 8 * (*recv_stride);
+    *recv_offset = 4096 + 2 * s;
+}
+
+bool launch_add_rmsnorm(const void *x, const void *residual, void *residual_out, const void *weight, void *normed,
+                        int64_t T, int64_t hidden, int64_t ldx, int64_t ldr, int64_t ldro, int64_t ldn, float eps,
+                        uint32_t dtype, void *p2p_region, int64_t p2p_slot_bytes, int world, cudaStream_t stream) {
+    if (T <= 0) return true;
+    if (dtype > 1 || hidden <= 0 || hidden % 8 || hidden > 8 * 512 * kNormMaxVec || (normed && !weight) ||
+        !al16(x) || !al16(residual) || !al16(residual_out) || !al16(weight) || !al16(normed) || ldx % 8 || ldr % 8 ||
+        ldro % 8 || ldn % 8 || (world > 1 && (!p2p_region || static_cast<int64_t>(T) * hidden * 2 > p2p_slot_bytes))) {
+        set_status(kErrInvalidArg,
+                   "atoma_add_rmsnorm: dtype 0=f16 1=bf16, hidden a multiple of 8 (<= %d), 16-byte aligned pointers and "
+                   "row strides (hidden %lld, dtype %u)",
+                   8 * 512 * kNormMaxVec, static_cast<long long>(hidden), dtype);
+        return false;
+    }
+    NormArgs a{};
+    a.x = x; a.residual = residual; a.residual_out = residual_out; a.weight = weight; a.normed = normed;
+    a.ldx = ldx; a.ldr = ldr; a.ldro = ldro; a.ldn = ldn;
+    a.hidden = static_cast<int>(hidden);
+    a.T = static_cast<int>(T);
+    a.eps = eps;
+    a.world = world > 1 ? world : 1;
+    a.region = static_cast<unsigned char *>(p2p_region);
+    if (a.world > 1) {
+        p2p_layout(p2p_slot_bytes, &a.recv_offset, &a.slot_stride, &a.recv_stride);
+        a.plane_bytes = static_cast<int64_t>(T) * hidden * 2;
+        a.timeout_ns = 30000000000ull;
+    }
+    const int nvec = a.hidden / 8;
+    int threads = std::min(512, (nvec + 31) / 32 * 32);
+    cudaError_t e = dtype == 1 ? launch_norm<__nv_bfloat16>(a, threads, stream) : launch_norm<__half>(a, threads, stream);
+    note_launch();
+    if (e != cudaSuccess) {
+        set_status(static_cast<int>(e), "add_rmsnorm_kernel: %s", cudaGetErrorString(e));
+        return false;
+    }
+    return check_launch("add_rmsnorm_kernel");
+}
+
+bool launch_embedding(const uint32_t *tokens, const void *table, void *out, int64_t T, int64_t hidden, int64_t vocab,
+                      int64_t ld_table, int64_t ldo, uint32_t dtype, cudaStream_t stream) {
+    if (T <= 0) return true;
+    if (dtype > 1 || hidden % 8 || !al16(table) || !al16(out) || ld_table % 8 || ldo % 8 || !tokens) {
+        set_status(kErrInvalidArg, "atoma_embedding: 16-bit dtype, hidden a multiple of 8, 16-byte aligned rows");
+        return false;
+    }
+    cudaError_t e;
+    if (dtype == 1)
+        e = launch_ex(embedding_kernel<__nv_bfloat16>, dim3(static_cast<unsigned>(T)), dim3(256), 0, stream, tokens,
+                      static_cast<const __nv_bfloat16 *>(table), static_cast<__nv_bfloat16 *>(out), static_cast<int>(hidden),
+                      ld_table, ldo, vocab);
+    else
+        e = launch_ex(embedding_kernel<__half>, dim3(static_cast<unsigned>(T)), dim3(256), 0, stream, tokens,
+                      static_cast<const __half *>(table), static_cast<__half *>(out), static_cast<int>(hidden), ld_table, ldo,
+                      vocab);
+    note_launch();
+    if (e != cudaSuccess) {
+        set_status(static_cast<int>(e), "embedding_kernel: %s", cudaGetErrorString(e));
+        return false;
+    }
+    return check_launch("embedding_kernel");
+}
+
+bool launch_argmax(const void *logits, int64_t T, int64_t vocab, int64_t ld, uint32_t dtype, uint32_t *token_out,
+                   float *logit_out, float *logits_f32, int64_t ld_f32, cudaStream_t stream) {
+    if (T <= 0) return true;
+    if (dtype > 1 || vocab <= 0 || !logits || !token_out || !al16(logits) || ld % 8 || (logits_f32 && (!al16(logits_f32) || ld_f32 % 4))) {
+        set_status(kErrInvalidArg, "atoma_sample_greedy: 16-bit logits with 16-byte aligned rows");
+        return false;
+    }
+    cudaError_t e;
+    if (dtype == 1)
+        e = launch_ex(argmax_kernel<__nv_bfloat16>, dim3(static_cast<unsigned>(T)), dim3(1024), 0, stream,
+                      static_cast<const __nv_bfloat16 *>(logits), ld, static_cast<int>(vocab), token_out, logit_out, logits_f32, ld_f32);
+    else
+        e = launch_ex(argmax_kernel<__half>, dim3(static_cast<unsigned>(T)), dim3(1024), 0, stream,
+                      static_cast<const __half *>(logits), ld, static_cast<int>(vocab), token_out, logit_out, logits_f32, ld_f32);
+    note_launch();
+    if (e != cudaSuccess) {
+        set_status(static_cast<int>(e), "argmax_kernel: %s", cudaGetErrorString(e));
+        return false;
+    }
+    return check_launch("argmax_kernel");
+}
+
+}  // namespace atoma

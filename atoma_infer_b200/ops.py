@@ -320,3 +320,117 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     _lib.lib().atoma_reset_launch_count()
+
+
+# ------------------------------------------------------------------------------------------------
+# decode-step operators (include/atoma_llama.h): what models/src/llama.rs issues as candle calls
+# ------------------------------------------------------------------------------------------------
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype not in (torch.float16, torch.bfloat16):
+        raise AtomaError("Only support f16/bf16 dtypes")
+    return 1 if t.dtype == torch.bfloat16 else 0
+
+
+def _raise_on_status() -> None:
+    L = _lib.lib()
+    if L.atoma_last_status() != 0:
+        raise AtomaError(L.atoma_last_error().decode())
+
+
+def gemm_tn(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y[T, N] = x[T, K] @ w[N, K]^T for f16/bf16 (`Linear::forward`, llama.rs:269-271, 311, 365, 476)."""
+    T, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((T, N), dtype=x.dtype, device=x.device)
+    _lib.lib().atoma_gemm_tn(x.data_ptr(), w.data_ptr(), out.data_ptr(), T, N, K, x.stride(0), w.stride(0),
+                             out.stride(0), _dt(x), _stream())
+    _raise_on_status()
+    return out
+
+
+def qkv_rope_cache(x, wqkv, num_heads: int, num_kv_heads: int, head_size: int, positions, cos, sin,
+                   key_cache=None, value_cache=None, slot_mapping=None, out=None) -> torch.Tensor:
+    """Fused q/k/v projection + RoPE + KV-cache write (llama.rs:269-304 + flash_attention.rs:361) ->
+    qkv [T, (H + 2 Hkv) D] with q and k rotated."""
+    T, K = x.shape
+    N = (num_heads + 2 * num_kv_heads) * head_size
+    if wqkv.shape[0] != N or wqkv.shape[1] != K:
+        raise AtomaError(f"wqkv must be [{N}, {K}], got {tuple(wqkv.shape)}")
+    if positions.dtype != torch.int64 or positions.numel() != T:
+        raise AtomaError(f"input_positions must be of dtype i64 and hold {T} positions")
+    if cos.dtype != x.dtype or sin.dtype != x.dtype or cos.shape[-1] != head_size // 2 or sin.shape != cos.shape:
+        raise AtomaError(f"cos/sin must be [max_pos, {head_size // 2}] tensors of the activation dtype")
+    if out is None:
+        out = torch.empty((T, N), dtype=x.dtype, device=x.device)
+    kc = vc = sm = None
+    block_stride = block_size = 0
+    if slot_mapping is not None and key_cache is not None:
+        if tuple(key_cache.shape[2:]) != (num_kv_heads, head_size) or value_cache.shape != key_cache.shape:
+            raise AtomaError(f"caches must be [num_blocks, block_size, {num_kv_heads}, {head_size}]")
+        if key_cache.stride(0) != value_cache.stride(0):
+            raise AtomaError("Only support block_stride == value_cache.stride[0]")
+        if slot_mapping.dtype != torch.int64 or slot_mapping.numel() != T:
+            raise AtomaError(f"slot_mapping must be of dtype i64 and hold {T} slots")
+        kc, vc, sm = key_cache.data_ptr(), value_cache.data_ptr(), slot_mapping.data_ptr()
+        block_stride, block_size = key_cache.stride(0), key_cache.shape[1]
+    _lib.lib().atoma_qkv_rope_cache(x.data_ptr(), wqkv.data_ptr(), out.data_ptr(), T, K, x.stride(0), wqkv.stride(0),
+                                    out.stride(0), num_heads, num_kv_heads, head_size, positions.data_ptr(),
+                                    cos.data_ptr(), sin.data_ptr(), cos.stride(0), sm, kc, vc, block_stride,
+                                    block_size, _dt(x), _stream())
+    _raise_on_status()
+    return out
+
+
+def gate_up_silu(x, w_gate_up, out=None) -> torch.Tensor:
+    """silu(x Wg^T) * (x Wu^T) with w_gate_up = cat([Wg, Wu]) (llama.rs:364)."""
+    T, K = x.shape
+    inter = w_gate_up.shape[0] // 2
+    if out is None:
+        out = torch.empty((T, inter), dtype=x.dtype, device=x.device)
+    _lib.lib().atoma_gate_up_silu(x.data_ptr(), w_gate_up.data_ptr(), out.data_ptr(), T, inter, K, x.stride(0),
+                                  w_gate_up.stride(0), out.stride(0), _dt(x), _stream())
+    _raise_on_status()
+    return out
+
+
+def add_rmsnorm(x, residual, weight, eps: float, residual_out=None, normed=None):
+    """h = x + residual (either may be None); returns (h, rmsnorm(h) * weight) — llama.rs:398-410."""
+    like = x if x is not None else residual
+    T, hidden = like.shape
+    if residual_out is None:
+        residual_out = torch.empty_like(like)
+    if normed is None and weight is not None:
+        normed = torch.empty_like(like)
+    p = lambda t: t.data_ptr() if t is not None else None
+    ld = lambda t: t.stride(0) if t is not None else hidden
+    _lib.lib().atoma_add_rmsnorm(p(x), p(residual), p(residual_out), p(weight), p(normed), T, hidden, ld(x),
+                                 ld(residual), ld(residual_out), ld(normed), eps, _dt(like), _stream())
+    _raise_on_status()
+    return residual_out, normed
+
+
+def embedding(tokens, table, out=None) -> torch.Tensor:
+    """table[tokens] (llama.rs:470); tokens: int32/uint32 bit patterns [T]."""
+    T = tokens.numel()
+    if tokens.dtype not in (torch.int32, getattr(torch, "uint32", torch.int32)):
+        raise AtomaError("token ids must be u32")
+    vocab, hidden = table.shape
+    if out is None:
+        out = torch.empty((T, hidden), dtype=table.dtype, device=table.device)
+    _lib.lib().atoma_embedding(tokens.data_ptr(), table.data_ptr(), out.data_ptr(), T, hidden, vocab, table.stride(0),
+                               out.stride(0), _dt(table), _stream())
+    _raise_on_status()
+    return out
+
+
+def sample_greedy(logits, want_f32: bool = False):
+    """(token ids int32 [T], their logits f32 [T], optional f32 copy of the logits) — model_executor.rs:227-262."""
+    T, vocab = logits.shape
+    tok = torch.empty((T,), dtype=torch.int32, device=logits.device)
+    val = torch.empty((T,), dtype=torch.float32, device=logits.device)
+    f32 = torch.empty((T, vocab), dtype=torch.float32, device=logits.device) if want_f32 else None
+    _lib.lib().atoma_sample_greedy(logits.data_ptr(), T, vocab, logits.stride(0), _dt(logits), tok.data_ptr(),
+                                   val.data_ptr(), f32.data_ptr() if f32 is not None else None, vocab, _stream())
+    _raise_on_status()
+    return tok, val, f32

@@ -11,7 +11,7 @@ import pytest
 from atoma_infer_b200 import _lib
 
 ROOT = Path(__file__).resolve().parent.parent
-HEADERS = [ROOT / "include" / "atoma_flash.h", ROOT / "include" / "atoma_ops.h"]
+HEADERS = sorted((ROOT / "include").glob("*.h"))
 REFERENCE_SYMBOLS = ["run_mha", "copy_blocks_f16", "copy_blocks_bf16", "reshape_and_cache_flash"]
 
 
