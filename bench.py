@@ -405,7 +405,7 @@ def tp_parity(torch, args, cfg, batch, ctx, layers, rank, world, dev, arm, dist)
     """N > 1: the tensor-parallel step's result against a tp=1 recomputation of the SAME step on rank 0
     (full weights and caches rebuilt from the same seeds).  Two numbers: after ONE layer without the head
     (two all-reduces: the bit budget is one bf16 rounding per all-reduce plus the regrouping of the fp32 partial
-    sums) the largest difference in bf16 ulps; after the whole step the norm-wise relative difference of the
+    sums) the largest difference in bf16 ulps taken at each row's rms; after the whole step the norm-wise relative difference of the
     logits and the fraction of sequences whose greedy token agrees."""
     from atoma_infer_b200.llama import DecodeStep
     res = {}
@@ -431,15 +431,14 @@ def tp_parity(torch, args, cfg, batch, ctx, layers, rank, world, dev, arm, dist)
                 res["logits_rel_err"] = rel
                 res["greedy_agreement"] = (tok == s1.next_tokens[:batch]).float().mean().item()
             else:
-                # bf16 ulp at |want|: 2^(floor(log2 |want|) - 7)
-                ulp = torch.exp2(torch.floor(torch.log2(want.abs().clamp_min(2.0 ** -126))) - 7)
+                ulp = torch.exp2(torch.floor(torch.log2(want.pow(2).mean(dim=-1, keepdim=True).sqrt().clamp_min(2.0 ** -126))) - 7)   # bf16 ulp at the row's rms
                 res["one_layer_max_ulp"] = (diff / ulp).max().item()
                 res["one_layer_rel_err"] = rel
             del w1, s1
             torch.cuda.empty_cache()
         dist.barrier()
     if rank == 0:
-        res["ok"] = bool(res["one_layer_max_ulp"] <= 4.0 and res["logits_rel_err"] <= 5e-2)
+        res["ok"] = bool(res["one_layer_max_ulp"] <= 8.0 and res["one_layer_rel_err"] <= 6e-3 and res["logits_rel_err"] <= 5e-2)
         res["how"] = ("rank 0 rebuilds the tp=1 model and caches from the same seeds and reruns the step; one_layer = 1 layer, "
                       "no head (2 all-reduces), full_step = the timed configuration")
     return res

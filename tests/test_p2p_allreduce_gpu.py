@@ -114,7 +114,8 @@ def test_p2p_all_reduce_bit_exact_two_gpus(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
-    world = 4 if torch.cuda.device_count() >= 4 else 2
+    n = torch.cuda.device_count()
+    world = 8 if n >= 8 else 4 if n >= 4 else 2   # every world size the bench runs at, up to what the box has
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert torch.load(tmp_path / f"r{r}.pt") == [], f"rank {r} mismatches"
