@@ -201,9 +201,12 @@ SIGNATURES = {
     "atoma_last_status": (C.c_int, []),
     "atoma_last_error": (C.c_char_p, []),
     "atoma_last_mha_path": (C.c_char_p, []),
+    "atoma_last_decode_mode": (C.c_int, []),
     "atoma_launch_count": (C.c_int64, []),
     "atoma_reset_launch_count": (None, []),
     "atoma_version": (C.c_char_p, []),
+    "atoma_source_hash": (C.c_char_p, []),
+    "atoma_mha_call_flags": (None, [C.c_int]),
     # atoma_llama.h
     "atoma_gemm_tn": (None, [C.c_void_p] * 3 + [C.c_int64] * 6 + [C.c_uint32, C.c_void_p]),
     "atoma_qkv_rope_cache": (None, [C.c_void_p] * 3 + [C.c_int64] * 8 + [C.c_void_p] * 3 + [C.c_int64] +
@@ -243,6 +246,20 @@ SIGNATURES = {
     "atoma_flash_attention_forward": (C.c_char_p, [C.POINTER(AttentionConfig)] + [C.POINTER(Tensor)] * 5 +
                                       [C.POINTER(AttentionMetadata), C.POINTER(Tensor), C.c_void_p]),
 }
+
+
+def source_hash() -> str:
+    """What csrc/Makefile compiles into atoma_source_hash(): SHA-256 (16 hex digits) of the library's sources,
+    csrc/ then include/, each in sorted order.  Equal to the loaded library's hash <=> the binary was built
+    from this tree."""
+    import hashlib
+    src = _PKG / "csrc"
+    files = sorted(str(p) for pat in ("*.cu", "*.cuh", "*.h", "*.cpp") for p in src.glob(pat))
+    files += sorted(str(p) for p in (_PKG.parent / "include").glob("*.h"))
+    h = hashlib.sha256()
+    for f in files:
+        h.update(Path(f).read_bytes())
+    return h.hexdigest()[:16]
 
 
 def load(path: os.PathLike | str | None = None) -> C.CDLL:

@@ -23,9 +23,13 @@
 //      local memory; 8-byte units are written atomically).
 //   3. Add the W addends in fp32 in RANK ORDER (bit-identical on every rank, run to run; NCCL's ring
 //      rounds to the 16-bit type at every hop) and write the local output.
-// Slots alternate between consecutive all-reduces: recv[slot] is overwritten by a peer's all-reduce
-// k+2 only after that peer finished k+1, which needed this rank's push of k+1, issued after this
-// rank's kernel k completed — so nothing is overwritten before it was read.
+// Receive buffers alternate between consecutive all-reduces — by the parity of the epoch, decided on the
+// DEVICE, so a captured graph with an odd number of all-reduces, or graphs replayed in any order, keep
+// alternating: recv[parity] is overwritten by a peer's all-reduce k+2 only after that peer finished k+1,
+// which needed this rank's push of k+1, issued after this rank's kernel k completed — so nothing is
+// overwritten before it was read.  (The staging slot the producer writes is the host's choice: it is local
+// and stream-ordered.)  The fused send/receive pair of gemm_skinny.cu + llama_ops.cu shares the epoch
+// counter and the receive buffers of this file.
 #include "common.cuh"
 
 #include "atoma_flash.h"
@@ -46,7 +50,9 @@ struct ArArgs {
     uint32_t *state;                     // local header
     void *out;
     int64_t stage_offset;                // byte offset of the staging slot inside a region
-    int64_t recv_offset;                 // byte offset of recv[slot][0] inside a region
+    int64_t recv_offset;                 // byte offset of recv[0][0] inside a region
+    int64_t recv_slot_stride;            // bytes between recv[0][..] and recv[1][..]; the receive slot of a launch
+                                         // is the parity of its epoch (device side: graphs replay in any order)
     int64_t recv_stride;                 // bytes between recv[slot][r] and recv[slot][r + 1]
     int64_t nvec;                        // 16-byte vectors
     int rank, world;
@@ -122,6 +128,7 @@ __global__ void __launch_bounds__(kArThreads) allreduce_p2p_kernel(const ArArgs 
     pdl_wait();
     const uint32_t e = a.state[0] + 1;   // this launch's epoch; advanced by the last CTA to finish
     if (a.state[2] != 0) return;          // a peer failed to arrive earlier: do not wait for it again
+    const int64_t recv_offset = a.recv_offset + (e & 1u) * a.recv_slot_stride;
     bool failed = false;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * kArThreads + tid; i < a.nvec;
          i += static_cast<int64_t>(gridDim.x) * kArThreads) {
@@ -131,7 +138,7 @@ __global__ void __launch_bounds__(kArThreads) allreduce_p2p_kernel(const ArArgs 
         for (int d = 1; d < W; ++d) {
             const int r = (a.rank + d) & (W - 1);   // start with the next rank: spreads the links
             // two planes of nvec 16-byte units: every warp-wide store covers 512 contiguous bytes
-            unsigned char *dst = a.region[r] + a.recv_offset + a.rank * a.recv_stride + i * 16;
+            unsigned char *dst = a.region[r] + recv_offset + a.rank * a.recv_stride + i * 16;
             st_relaxed_sys_v4(dst, mine.x, e, mine.y, e);
             st_relaxed_sys_v4(dst + a.nvec * 16, mine.z, e, mine.w, e);
         }
@@ -140,7 +147,7 @@ __global__ void __launch_bounds__(kArThreads) allreduce_p2p_kernel(const ArArgs 
         bool done[W];
 #pragma unroll
         for (int r = 0; r < W; ++r) done[r] = (r == a.rank);
-        const unsigned char *src = a.region[a.rank] + a.recv_offset + i * 16;
+        const unsigned char *src = a.region[a.rank] + recv_offset + i * 16;
         const unsigned long long t0 = ar_timer_ns();
         for (int spin = 0;; ++spin) {
             bool all = true;
@@ -195,6 +202,7 @@ __global__ void __launch_bounds__(kArThreads) allreduce_p2p_twoshot_kernel(const
     pdl_wait();
     const uint32_t e = a.state[0] + 1;
     if (a.state[2] != 0) return;
+    const int64_t recv_offset = a.recv_offset + (e & 1u) * a.recv_slot_stride;
     const int64_t chunk = (a.nvec + W - 1) / W;          // vectors per owner
     const int64_t half = a.recv_stride / 2;              // byte offset of the flight-2 area
     bool failed = false;
@@ -206,11 +214,11 @@ __global__ void __launch_bounds__(kArThreads) allreduce_p2p_twoshot_kernel(const
         const unsigned long long t0 = ar_timer_ns();
         if (owner != a.rank) {
             // flight 1: my addend to the owner
-            unsigned char *dst = a.region[owner] + a.recv_offset + a.rank * a.recv_stride + il * 16;
+            unsigned char *dst = a.region[owner] + recv_offset + a.rank * a.recv_stride + il * 16;
             st_relaxed_sys_v4(dst, mine.x, e, mine.y, e);
             st_relaxed_sys_v4(dst + chunk * 16, mine.z, e, mine.w, e);
             // flight 2: the finished vector from the owner
-            const unsigned char *src = a.region[a.rank] + a.recv_offset + owner * a.recv_stride + half + il * 16;
+            const unsigned char *src = a.region[a.rank] + recv_offset + owner * a.recv_stride + half + il * 16;
             uint4 lo, hi;
             for (int spin = 0;; ++spin) {
                 lo = ld_volatile_v4(src);
@@ -228,7 +236,7 @@ __global__ void __launch_bounds__(kArThreads) allreduce_p2p_twoshot_kernel(const
             bool done[W];
 #pragma unroll
             for (int r = 0; r < W; ++r) done[r] = (r == a.rank);
-            const unsigned char *src = a.region[a.rank] + a.recv_offset + il * 16;
+            const unsigned char *src = a.region[a.rank] + recv_offset + il * 16;
             for (int spin = 0;; ++spin) {
                 bool all = true;
 #pragma unroll
@@ -260,7 +268,7 @@ __global__ void __launch_bounds__(kArThreads) allreduce_p2p_twoshot_kernel(const
 #pragma unroll
             for (int d = 1; d < W; ++d) {
                 const int r = (a.rank + d) & (W - 1);
-                unsigned char *dst = a.region[r] + a.recv_offset + a.rank * a.recv_stride + half + il * 16;
+                unsigned char *dst = a.region[r] + recv_offset + a.rank * a.recv_stride + half + il * 16;
                 st_relaxed_sys_v4(dst, res.x, e, res.y, e);
                 st_relaxed_sys_v4(dst + chunk * 16, res.z, e, res.w, e);
             }
@@ -409,7 +417,8 @@ extern "C" void atoma_allreduce_sum_p2p(void *const *regions, int rank, int worl
     const int64_t s = slot_round(slot_bytes);
     a.stage_offset = static_cast<int64_t>(kArHeaderBytes) + (slot & 1) * s;
     a.recv_stride = 2 * s;
-    a.recv_offset = static_cast<int64_t>(kArHeaderBytes) + 2 * s + (slot & 1) * kArMaxWorld * a.recv_stride;
+    a.recv_slot_stride = kArMaxWorld * a.recv_stride;
+    a.recv_offset = static_cast<int64_t>(kArHeaderBytes) + 2 * s;
     a.nvec = count * esz / 16;
     a.rank = rank;
     a.world = world;

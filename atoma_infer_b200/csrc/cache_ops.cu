@@ -295,6 +295,7 @@ void copy_blocks_impl(void *key_cache_ptrs, void *value_cache_ptrs, const void *
                       cudaStream_t stream) {
     clear_status();
     if (num_layers <= 0 || num_pairs <= 0 || numel_per_block <= 0) return;
+    mark_cache_dirty(stream);   // whole pages are rewritten: the next decode on this stream must not run ahead
     if (num_pairs > 65535) {
         // gridDim.y limit; issue in slabs.
         const int64_t *bm = static_cast<const int64_t *>(block_mapping);
@@ -450,6 +451,7 @@ extern "C" void swap_blocks_batched(void *dst_base, const void *src_base,
     clear_status();
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (num_pairs <= 0 || block_bytes <= 0) return;
+    if (kind == 0 || kind == 1) mark_cache_dirty(stream);   // whole pages of a device cache are rewritten
     if (kind == 0) {
         // Device -> device: upload the mapping, one launch for all pairs.
         int64_t *dmap = static_cast<int64_t *>(

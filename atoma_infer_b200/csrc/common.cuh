@@ -26,6 +26,7 @@ void set_status(int code, const char *fmt, ...);
 void clear_status();
 void note_launch(int n = 1);
 void set_mha_path(const char *name);
+void note_decode_mode(int mode);   // bit 0: early KV streaming, bit 1: waited before releasing dependents
 bool check_launch(const char *what);  // cudaGetLastError -> status; true if ok
 
 struct DeviceInfo {
@@ -53,6 +54,8 @@ enum : int { kLaunchPdl = 1, kLaunchConstWeights = 2, kLaunchStableCache = 4 };
 int launch_flags();
 void set_next_decode_stable_cache(int v);   // per-call form of kLaunchStableCache (thread-local, one-shot)
 int take_next_decode_stable_cache();
+void mark_cache_dirty(cudaStream_t stream);   // a cache-maintenance op was enqueued on this stream
+bool take_cache_dirty(cudaStream_t stream);   // ... since the last paged decode launch on it?
 
 #if defined(__CUDACC__)
 // Kernel launch with the programmatic-stream-serialization attribute when PDL is enabled: the

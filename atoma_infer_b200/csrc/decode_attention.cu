@@ -73,7 +73,8 @@ struct DecodeArgs {
     int tb;          // tokens per TMA box (divides page and tok, multiple of 16)
     int g;           // query heads per kv head
     int num_ctas;
-    int early;       // PDL + ATOMA_LAUNCH_STABLE_CACHE: stream older pages before the grid dependency resolves
+    int early;       // PDL + the caller's per-call promise: stream older pages before the grid dependency resolves
+    int late_trigger;  // a cache-maintenance op is in flight on the stream: wait BEFORE releasing dependents
     int merged;      // map_k describes K AND V (one allocation, contiguous heads): one op moves both
     int *counters;   // [b * hg], zero between launches
     float *ws_ml;    // [cta][2][8 warps][16 rows][2]
@@ -234,8 +235,14 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
     // previous kernel in the stream has completed — except, in "stable cache" mode, what that kernel
     // cannot be writing: lengths, block tables and every page but the final one of a sequence.  The
     // producer warps then run up to a full ring (192 KiB per SM) ahead of the dependency.
-    pdl_launch_dependents();
-    if (!a.early) pdl_wait();
+    if (a.late_trigger) {
+        // a cache-maintenance op precedes this call: wait first, and only then let dependents start
+        pdl_wait();
+        pdl_launch_dependents();
+    } else {
+        pdl_launch_dependents();
+        if (!a.early) pdl_wait();
+    }
     if (a.trace && tid == 0) {
         a.trace[blockIdx.x * 8 + 0] = sm_id();
         a.trace[blockIdx.x * 8 + 1] = t_start;
@@ -868,7 +875,10 @@ int try_launch_decode_paged(const MhaParams &p, bool is_bf16, int64_t max_units_
     a.hkt = hkt; a.hg = hg; a.tok = tok; a.tb = tb; a.g = G;
     // early KV streaming needs PDL and the caller's promise for THIS call (or the legacy process-wide bit)
     const int stable_call = take_next_decode_stable_cache();
-    a.early = ((launch_flags() & kLaunchPdl) && (stable_call || (launch_flags() & kLaunchStableCache))) ? 1 : 0;
+    const bool dirty = take_cache_dirty(stream);   // copy_blocks / swap-in since the last decode on this stream
+    a.early = ((launch_flags() & kLaunchPdl) && stable_call && !dirty) ? 1 : 0;
+    a.late_trigger = dirty ? 1 : 0;
+    note_decode_mode(a.early | (a.late_trigger << 1));
     // Upper bound on units is known on the host only through seqlen_k (= pages * page size); the
     // kernel derives the real count from the device-side lengths.  Grid: one CTA per SM, but never
     // more CTAs than the upper bound of units.

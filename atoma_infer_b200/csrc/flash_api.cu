@@ -33,7 +33,9 @@ thread_local int t_status = 0;
 thread_local char t_error[512] = "";
 thread_local const char *t_path = "";
 thread_local int64_t t_launches = 0;
+thread_local int t_decode_mode = 0;
 }  // namespace
+void note_decode_mode(int mode) { t_decode_mode = mode; }
 
 namespace {
 std::atomic<int> g_launch_flags{0};
@@ -51,6 +53,35 @@ int take_next_decode_stable_cache() {
     const int v = t_next_stable_cache;
     t_next_stable_cache = 0;
     return v;
+}
+
+// Streams on which a cache-maintenance op (copy_blocks, swap-in) has been enqueued since the last paged
+// decode: such an op rewrites whole pages, which no "only final-page rows are being written" promise
+// covers.  The next decode launch on that stream ignores the promise, waits for its predecessors before
+// it touches anything AND before it lets its own dependents start (so that nothing downstream can run
+// ahead of the maintenance op either), and clears the mark.
+namespace {
+std::mutex g_dirty_mu;
+std::vector<std::pair<int, cudaStream_t>> g_dirty;
+}
+void mark_cache_dirty(cudaStream_t stream) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_dirty_mu);
+    for (const auto &e : g_dirty)
+        if (e.first == dev && e.second == stream) return;
+    g_dirty.emplace_back(dev, stream);
+}
+bool take_cache_dirty(cudaStream_t stream) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_dirty_mu);
+    for (size_t i = 0; i < g_dirty.size(); ++i)
+        if (g_dirty[i].first == dev && g_dirty[i].second == stream) {
+            g_dirty.erase(g_dirty.begin() + static_cast<long>(i));
+            return true;
+        }
+    return false;
 }
 
 void set_status(int code, const char *fmt, ...) {
@@ -168,10 +199,26 @@ void run_mha_impl(void *q_ptr, void *k_ptr, void *v_ptr, void *o_ptr, void *soft
                   uint32_t b, uint32_t h, uint32_t h_k, uint32_t d, float softmax_scale,
                   float scale_softmax_log2, int *block_table, uint32_t block_table_batch_stride,
                   int page_block_size, int *seqused_k, uint32_t seqlen_q, uint32_t seqlen_k,
-                  int is_bf16, int is_causal, bool unpadded_lse, cudaStream_t stream) {
+                  int is_bf16, int is_causal, bool unpadded_lse, int window_size_left, int window_size_right,
+                  float softcap, cudaStream_t stream) {
     clear_status();
     set_mha_path("none");
     if (b == 0 || h == 0 || seqlen_q == 0) return;
+    // The reference compiles sliding windows and soft-capping OUT (FLASHATTENTION_DISABLE_LOCAL / _SOFTCAP,
+    // static_switch.h:7-11) and silently computes full attention for them; so did round 1 of this library.
+    // A window that would actually mask something, or a soft cap, is refused instead of answered wrongly.
+    // (The tuples the reference's wrappers build for plain causal / full attention — window (seqlen_k, 0)
+    // or (-1, -1) — mask nothing beyond causality and pass.)
+    const bool left_masks = window_size_left >= 0 && static_cast<int64_t>(window_size_left) + 1 < static_cast<int64_t>(seqlen_k);
+    const bool right_masks = window_size_right >= 0 && !is_causal && seqlen_q > 1 &&
+                             static_cast<int64_t>(window_size_right) + 1 < static_cast<int64_t>(seqlen_k);
+    if (softcap > 0.f || left_masks || right_masks) {
+        set_status(kErrUnsupported,
+                   "run_mha: sliding-window (left %d, right %d) and soft-capped (softcap %g) attention are not implemented "
+                   "(the reference compiles both out and computes full attention); refusing to return an unmasked result",
+                   window_size_left, window_size_right, static_cast<double>(softcap));
+        return;
+    }
     if (!q_ptr || !k_ptr || !v_ptr || !o_ptr) {
         set_status(kErrInvalidArg, "run_mha: null q/k/v/o pointer");
         return;
@@ -258,8 +305,7 @@ extern "C" void run_mha(void *q_ptr, void *k_ptr, void *v_ptr, void *o_ptr, void
                         bool unpadded_lse, bool force_split_kernel, void *softmax_lseaccum_ptr,
                         void *oaccum_ptr) {
     (void)num_splits; (void)d_rounded; (void)seqlen_q_rounded; (void)seqlen_k_rounded;
-    (void)window_size_left; (void)window_size_right; (void)softcap; (void)force_split_kernel;
-    (void)softmax_lseaccum_ptr; (void)oaccum_ptr;
+    (void)force_split_kernel; (void)softmax_lseaccum_ptr; (void)oaccum_ptr;
     // Legacy default stream, as the reference (flash_api.cu:157).
     run_mha_impl(q_ptr, k_ptr, v_ptr, o_ptr, softmax_lse_ptr, alibi_slopes_ptr, cu_seqlens_q_ptr,
                  cu_seqlens_k_ptr, is_seqlens_k_cumulative, q_batch_stride, k_batch_stride,
@@ -267,7 +313,8 @@ extern "C" void run_mha(void *q_ptr, void *k_ptr, void *v_ptr, void *o_ptr, void
                  k_row_stride, v_row_stride, o_row_stride, q_head_stride, k_head_stride,
                  v_head_stride, o_head_stride, b, h, h_k, d, softmax_scale, scale_softmax_log2,
                  block_table, block_table_batch_stride, page_block_size, seqused_k, seqlen_q,
-                 seqlen_k, is_bf16, is_causal, unpadded_lse, static_cast<cudaStream_t>(0));
+                 seqlen_k, is_bf16, is_causal, unpadded_lse, window_size_left, window_size_right, softcap,
+                 static_cast<cudaStream_t>(0));
 }
 
 extern "C" void run_mha_stream(void *q_ptr, void *k_ptr, void *v_ptr, void *o_ptr,
@@ -290,15 +337,15 @@ extern "C" void run_mha_stream(void *q_ptr, void *k_ptr, void *v_ptr, void *o_pt
                                void *softmax_lseaccum_ptr, void *oaccum_ptr,
                                atoma_stream_t stream) {
     (void)num_splits; (void)d_rounded; (void)seqlen_q_rounded; (void)seqlen_k_rounded;
-    (void)window_size_left; (void)window_size_right; (void)softcap; (void)force_split_kernel;
-    (void)softmax_lseaccum_ptr; (void)oaccum_ptr;
+    (void)force_split_kernel; (void)softmax_lseaccum_ptr; (void)oaccum_ptr;
     run_mha_impl(q_ptr, k_ptr, v_ptr, o_ptr, softmax_lse_ptr, alibi_slopes_ptr, cu_seqlens_q_ptr,
                  cu_seqlens_k_ptr, is_seqlens_k_cumulative, q_batch_stride, k_batch_stride,
                  v_batch_stride, o_batch_stride, alibi_slopes_batch_stride, q_row_stride,
                  k_row_stride, v_row_stride, o_row_stride, q_head_stride, k_head_stride,
                  v_head_stride, o_head_stride, b, h, h_k, d, softmax_scale, scale_softmax_log2,
                  block_table, block_table_batch_stride, page_block_size, seqused_k, seqlen_q,
-                 seqlen_k, is_bf16, is_causal, unpadded_lse, static_cast<cudaStream_t>(stream));
+                 seqlen_k, is_bf16, is_causal, unpadded_lse, window_size_left, window_size_right, softcap,
+                 static_cast<cudaStream_t>(stream));
 }
 
 extern "C" void atoma_gemm_bf16_tn(const void *x, const void *w, void *y, int64_t T, int64_t N,
@@ -313,11 +360,24 @@ extern "C" void atoma_debug_gemm_trace(void *device_buf) { set_gemm_trace(device
 extern "C" void atoma_debug_decode_merge(int enable) { set_decode_merge(enable); }
 extern "C" void atoma_debug_gemm_stages(int stages) { set_gemm_stage_limit(stages); }
 extern "C" void atoma_debug_gemm_algo(int algo) { set_gemm_algo(algo); }
-extern "C" void atoma_set_launch_mode(int flags) { g_launch_flags.store(flags, std::memory_order_relaxed); }
+// ATOMA_LAUNCH_STABLE_CACHE is no longer honoured as a process-wide bit (a promise about what is in flight
+// on ONE stream before ONE call cannot be process-global state): it is masked off here; use
+// atoma_mha_call_flags(ATOMA_CALL_STABLE_CACHE) before the call it applies to.
+extern "C" void atoma_set_launch_mode(int flags) {
+    g_launch_flags.store(flags & (kLaunchPdl | kLaunchConstWeights), std::memory_order_relaxed);
+}
+extern "C" void atoma_mha_call_flags(int flags) { set_next_decode_stable_cache((flags & 1) ? 1 : 0); }
 extern "C" int atoma_get_launch_mode(void) { return launch_flags(); }
 extern "C" int atoma_last_status(void) { return t_status; }
 extern "C" const char *atoma_last_error(void) { return t_error; }
 extern "C" const char *atoma_last_mha_path(void) { return t_path; }
+extern "C" int atoma_last_decode_mode(void) { return t_decode_mode; }
 extern "C" int64_t atoma_launch_count(void) { return t_launches; }
 extern "C" void atoma_reset_launch_count(void) { t_launches = 0; }
-extern "C" const char *atoma_version(void) { return "atoma-flash-b200 0.1.0 (sm_100a)"; }
+#ifndef ATOMA_SOURCE_HASH
+#define ATOMA_SOURCE_HASH "unknown"
+#endif
+// The hash of the sources this binary was built from (csrc/Makefile): __graft_entry__.build() and smoke()
+// recompute it from the tree and refuse a library that was built from anything else.
+extern "C" const char *atoma_version(void) { return "atoma-flash-b200 0.2.0 (sm_100a) src:" ATOMA_SOURCE_HASH; }
+extern "C" const char *atoma_source_hash(void) { return ATOMA_SOURCE_HASH; }

@@ -111,73 +111,93 @@ gemm_tn_stream_kernel(const __grid_constant__ CUtensorMap map_w,
     const long long u_end = active ? g_cta_start(units, cta + 1, ncta) : 0;
     const int KB = a.kb_per_tile;
 
+    // Producer and MMA warps run converged on warp-uniform values with only the asynchronous instructions
+    // under elect.sync (see gemm_skinny.cu: inside `if (lane == 0)` every UTMALDG / UTCHMMA is wrapped in
+    // an R2UR + ELECT waterfall loop, ~70 cycles per MMA — more than a 128x128x16 MMA occupies the pipe).
     if (warp == 0) {
         // ============================ TMA producer ============================
-        if (lane == 0) {
-            pdl_launch_dependents();
-            // W is read once when there is a single activation chunk (decode): evict-first.  With
-            // several chunks every weight tile is re-read from L2 once per chunk: keep it.
-            const uint64_t w_policy = a.t_chunks == 1 ? kL2EvictFirst : kL2EvictLast;
-            int stage = 0;
-            uint32_t phase = 0;
-            long long u = u_begin;
-            // Programmatic dependent launch: W does not depend on the previous kernel, so the ring is
-            // filled with weight tiles while the predecessor drains; x (its output) follows the wait.
-            int pre = 0;
-            if (a.prefetch_w) {
-                pre = static_cast<int>(min(static_cast<long long>(a.stages), u_end - u_begin));
-                for (int i = 0; i < pre; ++i) {
-                    const long long uu = u_begin + i;
-                    const int tile = static_cast<int>(uu / KB), kb = static_cast<int>(uu % KB);
-                    mbar_arrive_expect_tx(&full[i], stage_bytes);
-                    tma_load_2d(tiles + i * stage_bytes, &map_w, &full[i], kb * kBlockK, (tile / a.t_chunks) * kTileN, w_policy);
+        pdl_launch_dependents();
+        // W is read once when there is a single activation chunk (decode): evict-first.  With
+        // several chunks every weight tile is re-read from L2 once per chunk: keep it.
+        const uint64_t w_policy = a.t_chunks == 1 ? kL2EvictFirst : kL2EvictLast;
+        // Programmatic dependent launch: W does not depend on the previous kernel, so the ring is
+        // filled with weight tiles while the predecessor drains; x (its output) follows the wait.
+        const int pre = a.prefetch_w ? static_cast<int>(min(static_cast<long long>(a.stages), u_end - u_begin)) : 0;
+        int tile = static_cast<int>(u_begin / KB), kb = static_cast<int>(u_begin % KB);   // running (tile, k block)
+        int n_tile = tile / a.t_chunks, t_chunk = tile % a.t_chunks;
+        auto advance = [&]() {
+            if (++kb == KB) {
+                kb = 0;
+                ++tile;
+                if (++t_chunk == a.t_chunks) {
+                    t_chunk = 0;
+                    ++n_tile;
                 }
             }
-            pdl_wait();
-            if (a.trace) a.trace[blockIdx.x * 4 + 0] = t_start;
+        };
+        if (pre > 0) {
+            const int tile0 = tile, kb0 = kb, n0 = n_tile, c0 = t_chunk;
             for (int i = 0; i < pre; ++i) {
-                const int tile = static_cast<int>((u_begin + i) / KB), kb = static_cast<int>((u_begin + i) % KB);
-                tma_load_2d(tiles + i * stage_bytes + kWBytes, &map_x, &full[i], kb * kBlockK,
-                            (tile % a.t_chunks) * a.t_pad, kL2EvictLast);
+                if (elect_one_sync()) {
+                    mbar_arrive_expect_tx(&full[i], stage_bytes);
+                    tma_load_2d(tiles + i * stage_bytes, &map_w, &full[i], kb * kBlockK, n_tile * kTileN, w_policy);
+                }
+                __syncwarp();
+                advance();
             }
-            u += pre;
-            stage = pre % a.stages;
-            phase = (pre == a.stages) ? 1u : 0u;
-            for (; u < u_end; ++u) {
-                const int tile = static_cast<int>(u / KB), kb = static_cast<int>(u % KB);
-                mbar_wait(&empty[stage], phase ^ 1);
-                unsigned char *ws = tiles + stage * stage_bytes;
+            tile = tile0; kb = kb0; n_tile = n0; t_chunk = c0;
+        }
+        pdl_wait();
+        if (a.trace && lane == 0) a.trace[blockIdx.x * 4 + 0] = t_start;
+        int stage = 0;
+        uint32_t phase = 0;
+        long long u = u_begin;
+        for (int i = 0; i < pre; ++i, ++u) {
+            if (elect_one_sync())
+                tma_load_2d(tiles + i * stage_bytes + kWBytes, &map_x, &full[i], kb * kBlockK, t_chunk * a.t_pad, kL2EvictLast);
+            __syncwarp();
+            advance();
+        }
+        stage = pre % a.stages;
+        phase = (pre == a.stages) ? 1u : 0u;
+        for (; u < u_end; ++u) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            unsigned char *ws = tiles + stage * stage_bytes;
+            if (elect_one_sync()) {
                 mbar_arrive_expect_tx(&full[stage], stage_bytes);
                 // W is read exactly once: evict-first; x is re-read by every CTA: keep it in L2.
-                tma_load_2d(ws, &map_w, &full[stage], kb * kBlockK, (tile / a.t_chunks) * kTileN, w_policy);
-                tma_load_2d(ws + kWBytes, &map_x, &full[stage], kb * kBlockK, (tile % a.t_chunks) * a.t_pad, kL2EvictLast);
-                if (++stage == a.stages) {
-                    stage = 0;
-                    phase ^= 1;
-                }
+                tma_load_2d(ws, &map_w, &full[stage], kb * kBlockK, n_tile * kTileN, w_policy);
+                tma_load_2d(ws + kWBytes, &map_x, &full[stage], kb * kBlockK, t_chunk * a.t_pad, kL2EvictLast);
+            }
+            __syncwarp();
+            advance();
+            if (++stage == a.stages) {
+                stage = 0;
+                phase ^= 1;
             }
         }
     } else if (warp == 1) {
         // ============================ MMA issuer ============================
         pdl_wait();
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(kTileN, a.t_pad, a.is_bf16 != 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            int seg = 0;
-            long long u = u_begin;
-            while (u < u_end) {
-                const int k0 = static_cast<int>(u % KB);
-                const int n = static_cast<int>(min(static_cast<long long>(KB - k0), u_end - u));
-                const int buf = seg & 1;
-                mbar_wait(&tempty[buf], ((seg >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+        const uint32_t idesc = umma_idesc_f16(kTileN, a.t_pad, a.is_bf16 != 0);
+        const uint32_t ring_u32 = smem_u32(tiles);
+        int stage = 0;
+        uint32_t phase = 0;
+        int seg = 0;
+        long long u = u_begin;
+        int k0 = static_cast<int>(u_begin % KB);
+        while (u < u_end) {
+            const int n = static_cast<int>(min(static_cast<long long>(KB - k0), u_end - u));
+            const int buf = seg & 1;
+            mbar_wait(&tempty[buf], ((seg >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+            tc_fence_after_sync();
+            const uint32_t tmem_d = tmem_base + buf * a.t_pad;
+            for (int i = 0; i < n; ++i) {
+                mbar_wait(&full[stage], phase);
                 tc_fence_after_sync();
-                const uint32_t tmem_d = tmem_base + buf * a.t_pad;
-                for (int i = 0; i < n; ++i) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after_sync();
-                    if (a.trace && seg == 0 && i == 0) a.trace[blockIdx.x * 4 + 1] = g_timer_ns();
-                    const uint32_t wa = smem_u32(tiles + stage * stage_bytes);
+                if (a.trace && seg == 0 && i == 0 && lane == 0) a.trace[blockIdx.x * 4 + 1] = g_timer_ns();
+                const uint32_t wa = ring_u32 + stage * stage_bytes;
+                if (elect_one_sync()) {
                     const uint64_t da = umma_desc_k_sw128(wa), db = umma_desc_k_sw128(wa + kWBytes);
 #pragma unroll
                     for (int k = 0; k < kBlockK / kUmmaK; ++k) {
@@ -185,15 +205,18 @@ gemm_tn_stream_kernel(const __grid_constant__ CUtensorMap map_w,
                         umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty[stage]);  // smem slot is free once these MMAs have read it
-                    if (++stage == a.stages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
                 }
-                umma_commit(&tfull[buf]);  // accumulator complete
-                ++seg;
-                u += n;
+                __syncwarp();
+                if (++stage == a.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
             }
+            if (elect_one_sync()) umma_commit(&tfull[buf]);  // accumulator complete
+            __syncwarp();
+            ++seg;
+            u += n;
+            k0 = 0;
         }
     } else {
         // ============================ epilogue warps (2..5) ============================

@@ -13,6 +13,8 @@
 #include "mha_params.h"
 #include "skinny_args.h"
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost nothing unless a tool (nsys, ncu) is attached
+
 #include <cmath>
 #include <cstring>
 
@@ -34,6 +36,15 @@ void set_next_decode_stable_cache(int v);
 namespace {
 
 inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// NVTX range for the lifetime of the object (the reference marks its forward passes with
+// tracing spans — models/src/llama.rs:258, 363, 397; these are the profiler-visible equivalent).
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 bool gemm_tn(const void *x, const void *w, void *y, int64_t T, int64_t N, int64_t K, int64_t ldx, int64_t ldw,
              int64_t ldy, uint32_t dtype, cudaStream_t stream) {
@@ -287,6 +298,7 @@ extern "C" void atoma_llama_decode_step(const atoma_llama_model *model, const at
                    static_cast<long long>(T));
         return;
     }
+    NvtxRange step_range("atoma_llama_decode_step");
     const Scratch s = carve(m, T, static_cast<char *>(b.scratch));
     const int64_t hid = m.hidden, H = m.num_heads, Hkv = m.num_kv_heads, D = m.head_dim;
     const int64_t nq = H * D, nqkv = (H + 2 * Hkv) * D;
@@ -302,6 +314,7 @@ extern "C" void atoma_llama_decode_step(const atoma_llama_model *model, const at
     }
     for (int64_t l = 0; l < m.num_layers; ++l) {
         const atoma_llama_layer &ly = m.layers[l];
+        NvtxRange layer_range("block");
         // residual += previous block's MLP output (all-reduced under TP); x = rms_1(residual)  (llama.rs:398-400)
         if (l == 0) {
             if (!launch_add_rmsnorm(nullptr, resid_in, s.resid, ly.rms_attn, s.normed, T, hid, hid, hid, hid, hid, m.rms_eps,

@@ -149,12 +149,13 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                                  int64_t rs, int row0, int len, int tma_row, int tma_head, int tma_batch,
                                  uint64_t policy) {
                 if (row0 + 128 <= len) {
-                    if (lane == 0) {
+                    if (elect_one_sync()) {
                         mbar_arrive_expect_tx(bar, C::kTileBytes);
 #pragma unroll
                         for (int hf = 0; hf < C::kHalves; ++hf)
                             tma_load_4d(dst + hf * C::kHalfBytes, map, bar, hf * 64, tma_head, tma_row, tma_batch, policy);
                     }
+                    __syncwarp();
                 } else {
                     for (int idx = lane; idx < 128 * (D / 8); idx += 32) {
                         const int r = idx / (D / 8), c = idx % (D / 8);
@@ -188,8 +189,13 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 load_tile(sv + s * C::kTileBytes, &map_v, &v_full[s], vg, p.v_rs, j * kPfN, len_k,
                           si.k_row0 + j * kPfN, kvh, si.k_batch, kL2EvictLast);
             }
-        } else if (warp == 1 && lane == 0 && n_max > 0) {
+        } else if (warp == 1 && n_max > 0) {
             // ================================ MMA issue ================================
+            // The whole warp runs this role converged on warp-uniform values; only the tcgen05
+            // instructions sit under elect.sync.  (Inside an `if (lane == 0)` region the compiler keeps
+            // the operands in vector registers and wraps every UTCHMMA in an R2UR + ELECT waterfall loop,
+            // ~70 cycles per MMA against the 64 cycles a 128x128x16 MMA occupies the tensor pipe — the
+            // issue thread, not the pipe, was the limit of round 1's kernel: tensor pipe 49 % active.)
             // Order per key tile j:  P.V(A,j)  QK(A,j+1)  P.V(B,j)  QK(B,j+1)
             // so while one query tile is being exponentiated the tensor pipe works for the other.
             constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
@@ -200,26 +206,32 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 const uint32_t q_addr = smem_u32(sq + t * C::kTileBytes);
                 const uint32_t k_addr = smem_u32(sk + s * C::kTileBytes);
                 const uint32_t tmem_s = tmem_base + t * 128;
+                if (elect_one_sync()) {
 #pragma unroll
-                for (int kk = 0; kk < D / 16; ++kk) {
-                    const uint32_t off = (kk >> 2) * C::kHalfBytes + (kk & 3) * 32;
-                    umma_f16_ss(tmem_s, umma_desc_k_sw128(q_addr + off), umma_desc_k_sw128(k_addr + off), idesc_qk,
-                                kk != 0 ? 1u : 0u);
+                    for (int kk = 0; kk < D / 16; ++kk) {
+                        const uint32_t off = (kk >> 2) * C::kHalfBytes + (kk & 3) * 32;
+                        umma_f16_ss(tmem_s, umma_desc_k_sw128(q_addr + off), umma_desc_k_sw128(k_addr + off), idesc_qk,
+                                    kk != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&s_full[t]);
                 }
-                umma_commit(&s_full[t]);
+                __syncwarp();
             };
             auto issue_pv = [&](int t, int j) {
                 const int s = j % kKvStages;
                 const uint32_t v_addr = smem_u32(sv + s * C::kTileBytes);
                 const uint32_t tmem_p = tmem_base + t * 128;
                 const uint32_t tmem_o = tmem_base + 256 + t * 128;
+                if (elect_one_sync()) {
 #pragma unroll
-                for (int kk = 0; kk < kPfN / 16; ++kk) {
-                    // 16 keys = 16 rows of 128 bytes of V; 16 P values = 8 packed 32-bit columns
-                    umma_f16_ts(tmem_o, tmem_p + kk * 8, umma_desc_mn_sw128(v_addr + kk * 16 * 128, C::kHalfBytes),
-                                idesc_pv, (j | kk) != 0 ? 1u : 0u);
+                    for (int kk = 0; kk < kPfN / 16; ++kk) {
+                        // 16 keys = 16 rows of 128 bytes of V; 16 P values = 8 packed 32-bit columns
+                        umma_f16_ts(tmem_o, tmem_p + kk * 8, umma_desc_mn_sw128(v_addr + kk * 16 * 128, C::kHalfBytes),
+                                    idesc_pv, (j | kk) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&pv_done[t]);
                 }
-                umma_commit(&pv_done[t]);
+                __syncwarp();
             };
             // first key tile: both query tiles
             mbar_wait(&k_full[0], 0);
@@ -231,7 +243,8 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     issue_qk(t, 0);
                 }
             }
-            umma_commit(&k_empty[0]);
+            if (elect_one_sync()) umma_commit(&k_empty[0]);
+            __syncwarp();
             for (int j = 0; j < n_max; ++j) {
                 const int s = j % kKvStages, sn = (j + 1) % kKvStages;
                 mbar_wait(&v_full[s], (j / kKvStages) & 1);
@@ -252,8 +265,11 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                         issue_qk(t, j + 1);
                     }
                 }
-                umma_commit(&v_empty[s]);                       // both P.V of tile j are issued
-                if (k_next_ready) umma_commit(&k_empty[sn]);    // ... and every QK^T of tile j + 1
+                if (elect_one_sync()) {
+                    umma_commit(&v_empty[s]);                       // both P.V of tile j are issued
+                    if (k_next_ready) umma_commit(&k_empty[sn]);    // ... and every QK^T of tile j + 1
+                }
+                __syncwarp();
             }
         }
     } else {

@@ -301,13 +301,26 @@ def gemm_bf16_tn(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] =
     return out
 
 
-LAUNCH_PDL, LAUNCH_CONST_WEIGHTS, LAUNCH_STABLE_CACHE = 1, 2, 4
+LAUNCH_PDL, LAUNCH_CONST_WEIGHTS = 1, 2
+CALL_STABLE_CACHE = 1
 
 
-def set_launch_mode(pdl: bool = False, const_weights: bool = False, stable_cache: bool = False) -> None:
-    """include/atoma_flash.h: atoma_set_launch_mode (process-wide)."""
-    _lib.lib().atoma_set_launch_mode((LAUNCH_PDL if pdl else 0) | (LAUNCH_CONST_WEIGHTS if const_weights else 0) |
-                                     (LAUNCH_STABLE_CACHE if stable_cache else 0))
+def set_launch_mode(pdl: bool = False, const_weights: bool = False) -> None:
+    """include/atoma_flash.h: atoma_set_launch_mode (process-wide: how kernels are launched, nothing about
+    what any particular call may assume)."""
+    _lib.lib().atoma_set_launch_mode((LAUNCH_PDL if pdl else 0) | (LAUNCH_CONST_WEIGHTS if const_weights else 0))
+
+
+def promise_stable_cache() -> None:
+    """include/atoma_flash.h: atoma_mha_call_flags(ATOMA_CALL_STABLE_CACHE) — for the NEXT attention call of
+    this thread only: whatever is still in flight on the stream writes nothing but final-page rows of the
+    sequences that call decodes."""
+    _lib.lib().atoma_mha_call_flags(CALL_STABLE_CACHE)
+
+
+def last_decode_mode() -> int:
+    """bit 0: the last paged decode streamed KV early; bit 1: it ran behind a cache-maintenance op."""
+    return _lib.lib().atoma_last_decode_mode()
 
 
 def last_mha_path() -> str:

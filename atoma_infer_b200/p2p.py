@@ -33,7 +33,9 @@ class _DeviceBuffer:
 class P2PComm:
     """One region per rank, mapped by every peer.  `slot(i, shape, dtype)` is where the producer
     (the o_proj GEMM) writes this rank's addend; `all_reduce(i, out)` sums slot i of every rank into
-    `out`.  Consecutive all-reduces must alternate i = 0, 1 (the kernel's reuse rule)."""
+    `out`.  i names the local staging slot only; which receive buffer an all-reduce uses is decided on the
+    device from the parity of its epoch, so any call order (and any number of all-reduces per captured
+    graph) is safe."""
 
     def __init__(self, rank: int, world: int, device: torch.device, slot_bytes: int, local: int, regions):
         self.rank, self.world, self.device, self.slot_bytes = rank, world, device, slot_bytes
@@ -86,9 +88,6 @@ class P2PComm:
         """out = sum over ranks of slot i (rank order, fp32 accumulation, one rounding)."""
         if out.dtype not in _DTYPES or not out.is_cuda or not out.is_contiguous():
             raise P2PError("all_reduce needs a contiguous f16/bf16/f32 CUDA tensor (multi_gpu.rs:146-178)")
-        if self._last_slot is not None and (i & 1) == self._last_slot:
-            raise P2PError("consecutive all-reduces must alternate slots 0 and 1")
-        self._last_slot = i & 1
         if stream is None:
             stream = torch.cuda.current_stream(out.device).cuda_stream
         L = _lib.lib()

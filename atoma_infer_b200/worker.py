@@ -57,16 +57,30 @@ class InputStager:
         self.device = torch.device(device) if device is not None else None
         self.block_size, self.sliding_window = block_size, sliding_window
         self.enable_chunked_prefill = enable_chunked_prefill
-        self._host = self._dev = None
+        self._hosts = self._dev = None
+        self._events = [None, None]
+        self._turn = 0
+        self.generation = 0          # bumped whenever the device image is reallocated (views taken earlier are dead)
         self._reserve(initial_bytes)
 
+    @property
+    def _host(self) -> torch.Tensor:
+        return self._hosts[self._turn]
+
     def _reserve(self, nbytes: int) -> None:
-        if self._host is not None and self._host.numel() >= nbytes:
+        """Two pinned staging buffers (so that step k+1 can be marshalled while step k's copy is still queued)
+        and one device image."""
+        if self._hosts is not None and self._hosts[0].numel() >= nbytes:
             return
         cap = 1 << max(12, (int(nbytes) - 1).bit_length())
-        pin = self.device is not None and self.device.type == "cuda"
-        self._host = torch.empty(cap, dtype=torch.uint8, pin_memory=pin)
-        self._dev = torch.empty(cap, dtype=torch.uint8, device=self.device) if self.device is not None else self._host
+        cuda = self.device is not None and self.device.type == "cuda"
+        if self._hosts is not None and cuda:
+            torch.cuda.synchronize(self.device)      # queued copies still read the old buffers
+        self._hosts = [torch.empty(cap, dtype=torch.uint8, pin_memory=cuda) for _ in range(2 if cuda else 1)]
+        self._events = [None] * len(self._hosts)
+        self._turn = 0
+        self._dev = torch.empty(cap, dtype=torch.uint8, device=self.device) if self.device is not None else self._hosts[0]
+        self.generation += 1
 
     def _marshal(self, seqs: Seq_[SequenceInput]):
         arr = (Sequence * len(seqs))()
@@ -100,19 +114,33 @@ class InputStager:
         return self.prepare_marshalled(self._marshal(seqs), prefix_caching)
 
     def prepare_marshalled(self, handle, prefix_caching: bool = False) -> ModelInput:
-        return self._views(self.refresh(handle), prefix_caching)
+        return self._views(self._fill(handle, allow_grow=True), prefix_caching)
 
     def refresh(self, handle) -> ModelInputLayout:
-        """Rebuilds the step's tensors in the pinned buffer and ships them with one copy; returns the
+        """Rebuilds the step's tensors in a pinned buffer and ships them with one copy; returns the
         layout only.  For steady-state steps whose tensor views were taken earlier (same shapes ->
-        same offsets; the caller may compare `total_bytes` and the counts)."""
+        same offsets; the caller may compare `total_bytes` and the counts).  The device image is never
+        reallocated here: a step that no longer fits raises (views and captured graphs over the old
+        image would silently go stale) — call prepare_input_tensors again and re-capture."""
+        return self._fill(handle, allow_grow=False)
+
+    def _fill(self, handle, allow_grow: bool) -> ModelInputLayout:
         L = _lib.lib()
         arr, _keep = handle
         lay = ModelInputLayout()
         args = (arr, len(arr), self.block_size, int(self.sliding_window or 0), 1 if self.enable_chunked_prefill else 0)
+        # The staging buffers alternate; before one is rewritten, the copy that last read it must have
+        # executed (an asynchronous copy reads pinned memory when it RUNS, not when it is enqueued).
+        self._turn = (self._turn + 1) % len(self._hosts)
+        if self._events[self._turn] is not None:
+            self._events[self._turn].synchronize()
         # one call computes the layout and fills the buffer; grow and retry if it did not fit
         err = L.atoma_prepare_input(*args, C.byref(lay), self._host.data_ptr(), self._host.numel())
         if err and lay.total_bytes > self._host.numel():
+            if not allow_grow:
+                raise AtomaError(f"step inputs need {int(lay.total_bytes)} bytes but the staging image holds "
+                                 f"{self._host.numel()}: views taken earlier (and graphs captured over them) would go "
+                                 "stale; call prepare_input_tensors() again and re-capture")
             self._reserve(lay.total_bytes)
             err = L.atoma_prepare_input(*args, C.byref(lay), self._host.data_ptr(), self._host.numel())
         if err:
@@ -120,6 +148,9 @@ class InputStager:
         if self._dev is not self._host:   # THE host-to-device copy of the step
             n = int(lay.total_bytes)
             self._dev[:n].copy_(self._host[:n], non_blocking=True)
+            ev = self._events[self._turn] or torch.cuda.Event()
+            ev.record()
+            self._events[self._turn] = ev
         return lay
 
     def _views(self, lay: ModelInputLayout, prefix_caching: bool) -> ModelInput:

@@ -141,9 +141,11 @@ void atoma_rope_reshape_and_cache(void *q, void *k, void *v, void *key_cache, vo
 /*
  * Batched block swap: for p < num_pairs copy block_bytes bytes from
  * src_base + src_blocks[p]*block_bytes to dst_base + dst_blocks[p]*block_bytes.
- * kind: 0 = device->device (one kernel launch, 16-byte vectors; src_blocks/dst_blocks are HOST
- * arrays, uploaded by the call), 1 = host->device, 2 = device->host (contiguous runs of blocks
- * are coalesced into single async copies on `stream`; the host side should be pinned).
+ * kind: 0 = device->device (one launch of the bulk-copy kernel, cp.async.bulk through shared memory;
+ * src_blocks/dst_blocks are HOST arrays, uploaded by the call), 1 = host->device, 2 = device->host: with
+ * pinned (device-mapped) host memory the SAME kernel reads / writes the host buffer over the host link in
+ * one launch, scattered blocks included; with pageable host memory contiguous runs of blocks are merged
+ * into single cudaMemcpyAsync calls on `stream`.
  * Replaces the per-block memcpy loop of csrc/src/cache_manager.rs:18-128 + ops.rs:16-220, which
  * has no C symbol in the reference.
  */
@@ -201,23 +203,33 @@ void atoma_debug_allreduce_algo(int algo);
  *   ATOMA_LAUNCH_CONST_WEIGHTS (2) the `w` operand of atoma_gemm_bf16_tn is never written by work
  *                                  in flight on the stream (inference weights): with PDL the GEMM
  *                                  starts streaming W into shared memory before the predecessor ends.
- *   ATOMA_LAUNCH_STABLE_CACHE (4)  for paged decode calls (run_mha with a block table and seqlen_q == 1):
- *                                  the work still in flight on the stream when the call is made writes
- *                                  no sequence length, no block-table entry and, in the pages this call's
- *                                  block tables reference, no cache row other than rows of each
- *                                  sequence's FINAL page (the slot of the token being
- *                                  decoded: reshape_and_cache_flash / atoma_rope_reshape_and_cache just
- *                                  before the attention call, flash_attention.rs:361 then :455; pages
- *                                  are exclusive to a sequence while they are written — copy-on-write).
- *                                  With PDL the decode kernel then streams all older pages while its
- *                                  predecessor (the cache write) is still running, and waits for it
- *                                  only before it loads q, the final page of a sequence, or writes.
+ *   (4, formerly ATOMA_LAUNCH_STABLE_CACHE, is ignored: that promise is per call, see below.)
  */
 #define ATOMA_LAUNCH_PDL 1
 #define ATOMA_LAUNCH_CONST_WEIGHTS 2
-#define ATOMA_LAUNCH_STABLE_CACHE 4
+#define ATOMA_LAUNCH_STABLE_CACHE 4 /* deprecated, masked off by atoma_set_launch_mode */
 void atoma_set_launch_mode(int flags);
 int atoma_get_launch_mode(void);
+
+/*
+ * Per-call flags for the NEXT run_mha / run_mha_stream / atoma_mha_execute call made by the calling thread
+ * (one-shot: consumed by that call, thread-local — no process-global state):
+ *   ATOMA_CALL_STABLE_CACHE (1)  for a paged decode call (block table, seqlen_q == 1): the work still in
+ *       flight on the call's stream writes no sequence length, no block-table entry and, in the pages this
+ *       call's block tables reference, no cache row other than rows of each sequence's FINAL page (the slot
+ *       of the token being decoded: reshape_and_cache_flash / atoma_rope_reshape_and_cache /
+ *       atoma_qkv_rope_cache just before the attention call, flash_attention.rs:361 then :455; pages are
+ *       exclusive to a sequence while they are written — copy-on-write).  With PDL the decode kernel then
+ *       streams all older pages while its predecessor (the cache write) is still running and waits for it
+ *       only before it loads q, the final page of a sequence, or writes.
+ * The library itself withdraws the promise where it can see it broken: copy_blocks_f16/bf16 and
+ * swap_blocks_batched into a device cache mark their stream, and the next paged decode launched on a marked
+ * stream ignores the flag, waits for everything before it BEFORE releasing its own dependents, and clears
+ * the mark.  atoma_llama_decode_step sets the flag itself for its attention calls (it knows the predecessor
+ * is its own qkv projection).
+ */
+#define ATOMA_CALL_STABLE_CACHE 1
+void atoma_mha_call_flags(int flags);
 
 /* Diagnostics: when device_buf is non-null every CTA of the paged decode kernel writes eight
  * uint64 {sm id, start, end of its last KV segment, end, partial published, arrival counted,
@@ -242,11 +254,18 @@ int atoma_last_status(void);
 const char *atoma_last_error(void);
 /* Name of the kernel path the last run_mha on this thread dispatched to (for tests/bench). */
 const char *atoma_last_mha_path(void);
+/* How the last paged decode launch of this thread ran: bit 0 = early KV streaming (ATOMA_CALL_STABLE_CACHE
+ * honoured), bit 1 = a cache-maintenance op was pending on the stream, so the kernel waited for its
+ * predecessors before releasing its dependents and the promise was ignored. */
+int atoma_last_decode_mode(void);
 /* Number of kernels launched by this library on this thread since the last reset. */
 int64_t atoma_launch_count(void);
 void atoma_reset_launch_count(void);
-/* Library version string. */
+/* Library version string; ends in "src:<hash>" = atoma_source_hash(). */
 const char *atoma_version(void);
+/* SHA-256 (first 16 hex digits) of the sources the library was built from (csrc/Makefile computes it over
+ * csrc/ and include/ in sorted order); __graft_entry__.build() and smoke() check it against the tree. */
+const char *atoma_source_hash(void);
 
 #ifdef __cplusplus
 }

@@ -70,9 +70,32 @@ def test_version_and_status_calls_work_without_a_gpu():
 
 
 def test_sass_is_blackwell_native():
-    """The decode kernel must carry TMA (UTMALDG) and the library must be built for sm_100a."""
+    """Built for sm_100a, and the SASS carries what B200_PROFILING.md lists as proof of a Blackwell-native
+    kernel: TMA tensor loads (UTMALDG), bulk async copies (UBLKCP), tcgen05.mma (UTCHMMA) with accumulators
+    read back from tensor memory (LDTM) — per kernel family, not just somewhere in the library."""
     out = subprocess.run(["cuobjdump", "-lelf", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     sass = subprocess.run(["cuobjdump", "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
-    assert "UTMALDG" in sass, "no TMA tensor loads in the library SASS"
-    assert "UBLKCP" in sass, "no bulk async copies (copy_blocks) in the library SASS"
+    per_kernel, name = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :")[1].strip()
+            per_kernel[name] = set()
+        elif name is not None:
+            for op in ("UTMALDG", "UBLKCP", "UTCHMMA", "LDTM", "STTM", "HMMA", "UTCBAR"):
+                if op in line:
+                    per_kernel[name].add(op)
+    fam = lambda key: set().union(*[ops for n, ops in per_kernel.items() if key in n])
+    assert {"UTMALDG", "UTCHMMA", "LDTM", "UTCBAR"} <= fam("gemm_skinny_kernel"), fam("gemm_skinny_kernel")
+    assert {"UTMALDG", "UTCHMMA", "LDTM"} <= fam("gemm_tn_stream_kernel")
+    assert {"UTMALDG", "UTCHMMA", "LDTM", "STTM"} <= fam("prefill_attn_kernel")
+    assert {"UTMALDG", "HMMA"} <= fam("decode_paged_kernel")      # GQA rows cannot fill a 128-row tcgen05 tile
+    assert "UBLKCP" in fam("copy_blocks_bulk_kernel")
+
+
+def test_library_matches_the_source_tree():
+    """atoma_source_hash() (compiled in by csrc/Makefile) == the hash of the sources in the tree: the binary the
+    tests load was built from exactly these files."""
+    L = _lib.lib()
+    assert L.atoma_source_hash().decode() == _lib.source_hash()
+    assert L.atoma_version().decode().endswith("src:" + _lib.source_hash())

@@ -143,3 +143,22 @@ def test_one_copy_ships_the_step_to_the_gpu():
     torch.cuda.synchronize()
     assert mi.attention_metadata.slot_mapping.is_cuda
     _check(mi, orc.prepare_input_tensors(so, 16, None, True))
+
+
+def test_refresh_never_reallocates_the_staging_image():
+    """Round-1 advisor (medium): refresh() used to swap the host / device images when a step outgrew them,
+    leaving views handed out earlier (and graphs captured over them) pointing at a dead image.  Now only
+    prepare_input_tensors() may grow (new views, `generation` bumped); refresh() raises."""
+    from atoma_infer_b200.ops import AtomaError
+    InputStager, SequenceInput = worker.InputStager, worker.SequenceInput
+    st = InputStager(None, 16, initial_bytes=4096)
+    small = [SequenceInput(np.arange(20, dtype=np.uint32), 0, 1, np.arange(2, dtype=np.uint32), False)]
+    mi = st.prepare_input_tensors(small)
+    gen = st.generation
+    assert st.refresh(st.marshal(small)).total_bytes == mi.layout.total_bytes and st.generation == gen
+    big = [SequenceInput(np.arange(5000, dtype=np.uint32), 0, 1, np.arange(400, dtype=np.uint32), False) for _ in range(8)]
+    with pytest.raises(AtomaError, match="views taken earlier"):
+        st.refresh(st.marshal(big))
+    assert st.generation == gen
+    mi2 = st.prepare_input_tensors(big)          # allowed to grow: hands out fresh views
+    assert st.generation == gen + 1 and mi2.attention_metadata.decoding_metadata.block_tables.shape == (8, 400)

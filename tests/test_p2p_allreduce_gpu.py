@@ -72,17 +72,19 @@ def _worker(rank, world, port, out_dir):
     k += 1
     if not torch.equal(o2.cpu(), _want(parts, torch.bfloat16)):
         bad.append(("ragged",))
-    # same slot twice in a row is refused on the host
-    try:
-        comm.all_reduce((k - 1) % 2, o2)
-        bad.append(("slot reuse accepted",))
-    except P2PError:
-        pass
-    # CUDA graph: 8 (copy-in, all-reduce) pairs, replayed 3 times, once per algorithm
+    # the same staging slot twice in a row: the receive buffer is chosen on the device (epoch parity)
+    for rep in range(3):
+        parts = _addends(world, (1000,), torch.bfloat16, 90 + rep)
+        comm.slot(0, (1000,), torch.bfloat16).copy_(parts[rank].to(dev))
+        comm.all_reduce(0, o2)
+        if not torch.equal(o2.cpu(), _want(parts, torch.bfloat16)):
+            bad.append(("same staging slot", rep))
+    # CUDA graph: 7 (copy-in, all-reduce) pairs — an ODD count — replayed 3 times, once per algorithm
     dtype = torch.bfloat16
-    srcs = [p[rank].to(dev) for p in (_addends(world, shape, dtype, 200 + i) for i in range(8))]
-    wants = [_want(_addends(world, shape, dtype, 200 + i), dtype) for i in range(8)]
-    outs = [torch.empty(shape, dtype=dtype, device=dev) for _ in range(8)]
+    NG = 7
+    srcs = [p[rank].to(dev) for p in (_addends(world, shape, dtype, 200 + i) for i in range(NG))]
+    wants = [_want(_addends(world, shape, dtype, 200 + i), dtype) for i in range(NG)]
+    outs = [torch.empty(shape, dtype=dtype, device=dev) for _ in range(NG)]
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     torch.cuda.synchronize()
@@ -90,7 +92,7 @@ def _worker(rank, world, port, out_dir):
         _lib.lib().atoma_debug_allreduce_algo(algo)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=s):
-            for i in range(8):
+            for i in range(NG):
                 comm.slot((k + i) % 2, shape, dtype).copy_(srcs[i])
                 comm.all_reduce((k + i) % 2, outs[i])
         for rep in range(3):
@@ -98,7 +100,7 @@ def _worker(rank, world, port, out_dir):
                 o.zero_()
             g.replay()
             torch.cuda.synchronize()
-            for i in range(8):
+            for i in range(NG):
                 if not torch.equal(outs[i].cpu(), wants[i]):
                     bad.append(("graph", algo, rep, i))
         del g

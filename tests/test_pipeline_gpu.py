@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _chain(layers, x, wqkv, wo, kv, bt, lens, slots, H, HK, D):
+def _chain(layers, x, wqkv, wo, kv, bt, lens, slots, H, HK, D, stable=False):
     nq, nkv = H * D, HK * D
     B = x.shape[0]
     for l in range(layers):
@@ -22,6 +22,8 @@ def _chain(layers, x, wqkv, wo, kv, bt, lens, slots, H, HK, D):
         k = qkv[:, nq:nq + nkv].unflatten(1, (HK, D))
         v = qkv[:, nq + nkv:].unflatten(1, (HK, D))
         ops.reshape_and_cache_flash(k, v, kv[l][0], kv[l][1], slots)
+        if stable:
+            ops.promise_stable_cache()   # per call: the cache write above touches only final-page slots
         o = ops.flash_attn_kv_cache_full(q, kv[l][0], kv[l][1], None, D ** -0.5, bt, lens, True)
         x = ops.gemm_bf16_tn(o.reshape(B, nq), wo[l])
     return x
@@ -46,9 +48,10 @@ def state():
 
 
 def _run(st, pdl, const_w, graph, stable_cache=False):
-    ops.set_launch_mode(pdl, const_w, stable_cache)
+    ops.set_launch_mode(pdl, const_w)
     kv = [c.clone() for c in st["kv0"]]
-    args = (st["layers"], st["x"], st["wqkv"], st["wo"], kv, st["bt"], st["lens"], st["slots"], st["H"], st["HK"], st["D"])
+    args = (st["layers"], st["x"], st["wqkv"], st["wo"], kv, st["bt"], st["lens"], st["slots"], st["H"], st["HK"], st["D"],
+            stable_cache)
     if not graph:
         out = _chain(*args)
         torch.cuda.synchronize()
@@ -77,3 +80,40 @@ def test_chain_pdl_and_graph_variants_are_bit_identical(state):
         assert torch.equal(out, base), f"pdl={pdl} const_weights={cw} graph={graph} stable_cache={sc}"
         for a, b in zip(kv, kv_base):
             assert torch.equal(a, b)
+
+
+def test_stable_cache_promise_is_per_call_and_withdrawn_after_cache_maintenance(state):
+    """The early-KV-streaming promise is one-shot and per call (no process-global bit), needs PDL, and the
+    library withdraws it by itself when a cache-maintenance op (copy_blocks) is pending on the stream: that
+    decode waits for its predecessors before releasing its dependents (bit 1) and reads the copied pages."""
+    st = state
+    H, HK, D = st["H"], st["HK"], st["D"]
+    kv = st["kv0"][0].clone()
+    q = randn_t((st["x"].shape[0], 1, H, D), 77, torch.bfloat16, DEV)
+    call = lambda: ops.flash_attn_kv_cache_full(q, kv[0], kv[1], None, D ** -0.5, st["bt"], st["lens"], True)
+    ops.set_launch_mode(True, True)
+    base = call()
+    assert ops.last_decode_mode() == 0                      # no promise -> no early streaming
+    ops.promise_stable_cache()
+    assert torch.equal(call(), base) and ops.last_decode_mode() == 1
+    assert torch.equal(call(), base) and ops.last_decode_mode() == 0   # one-shot
+    ops.set_launch_mode(False, False)
+    ops.promise_stable_cache()
+    assert torch.equal(call(), base) and ops.last_decode_mode() == 0   # needs programmatic dependent launch
+    # copy the first page of sequence 0 somewhere else and point the block table at the copy
+    ops.set_launch_mode(True, True)
+    bt = st["bt"].clone()
+    src = int(bt[0, 0])
+    used = set(bt.flatten().tolist())
+    dst = next(i for i in range(kv.shape[1]) if i not in used)
+    kv[:, dst] = 0
+    mapping = torch.tensor([[src, dst]], dtype=torch.int64, device=DEV)
+    ops.copy_blocks([kv[0]], [kv[1]], mapping)
+    bt[0, 0] = dst
+    ops.promise_stable_cache()                              # a promise the library knows to be false here
+    out = ops.flash_attn_kv_cache_full(q, kv[0], kv[1], None, D ** -0.5, bt, st["lens"], True)
+    assert ops.last_decode_mode() == 2
+    torch.cuda.synchronize()
+    assert torch.equal(out, base)
+    ops.promise_stable_cache()
+    assert torch.equal(call(), base) and ops.last_decode_mode() == 1   # the mark is cleared by the decode that honoured it
