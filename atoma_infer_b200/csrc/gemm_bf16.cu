@@ -35,7 +35,6 @@ constexpr int kMaxTPad = 256;     // activation rows per tile (UMMA N); larger T
 constexpr int kMaxStages = 12;
 constexpr int kGemmMaxCtas = 256;
 constexpr int kWBytes = kTileN * kBlockK * 2;  // 16 KiB
-constexpr int kMaxTPadCluster = 64;            // cluster variant: accumulator row kept in registers
 
 struct GemmArgs {
     void *y;
@@ -51,8 +50,6 @@ struct GemmArgs {
     int *counters;    // [tiles], zero between launches
     float *ws;        // [cta][2][t_pad][128] fp32 partials
     int prefetch_w;   // W is immutable: stream it before the grid dependency resolves
-    int csize;        // cluster variant: CTAs per weight tile (the k range is split evenly among them)
-    int red_off;      // cluster variant: byte offset of the leader's reduction buffer behind the ring
     unsigned long long *trace;  // diagnostics (atoma_debug_gemm_trace): [cta][4] or null
 };
 
@@ -368,160 +365,6 @@ gemm_tn_stream_kernel(const __grid_constant__ CUtensorMap map_w,
 
 
 // ---------------------------------------------------------------------------------------------
-// EXPERIMENTAL (opt-in through atoma_debug_gemm_algo(1); written at the end of round 1: parity-green
-// on a B200 in its one run — o_proj 15.9 us vs 17.5 us stream-K, cuBLAS 10.1 — but not yet tuned or
-// profiled): fixed split per tile, reduced through distributed shared memory.  The stream-K kernel above loses ~4.5 us per launch in its tail (partials through L2, fence,
-// arrival counter, last-arriver reduction — scripts/trace_gemm_pair.py).  Here a thread-block cluster
-// of `csize` CTAs owns one 128-row weight tile, CTA r streams the r-th part of K, and the partial
-// accumulators of CTAs 1.. are written straight into CTA 0's shared memory (st.shared::cluster),
-// followed by ONE cluster barrier; CTA 0 adds them to its own accumulator in rank order
-// (deterministic) and stores the tile.  No workspace, no atomics, no second segment per CTA.
-// Decode shapes only (one activation chunk of <= 64 rows).
-template <int TP>   // TP = a.t_pad (16, 32, 48 or 64): the accumulator row lives in registers
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tn_cluster_kernel(const __grid_constant__ CUtensorMap map_w,
-                       const __grid_constant__ CUtensorMap map_x, const GemmArgs a) {
-    extern __shared__ unsigned char smem_dyn[];
-    unsigned char *tiles = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-    __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], tfull;
-    __shared__ uint32_t tmem_base_smem;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int x_bytes = TP * 128;
-    constexpr int stage_bytes = kWBytes + x_bytes;
-    const int rank = static_cast<int>(cluster_ctarank());
-    const int tile = blockIdx.x / a.csize;            // cluster dims (csize, 1, 1): consecutive CTAs
-    const int KB = a.kb_per_tile;
-    const int kb0 = KB * rank / a.csize, kb1 = KB * (rank + 1) / a.csize;
-    const int nkb = kb1 - kb0;                        // >= 1 (host: KB >= csize)
-
-    if (tid == 0) {
-        for (int i = 0; i < a.stages; ++i) {
-            mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
-        }
-        mbar_init(&tfull, 1);
-        fence_mbar_init();
-        tma_prefetch_desc(&map_w);
-        tma_prefetch_desc(&map_x);
-    }
-    if (warp == 1) tmem_alloc(&tmem_base_smem, a.tmem_cols);
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem_base = tmem_base_smem;
-    // Phase 1 of the cluster barrier: "this CTA is running" (distributed shared memory of a CTA may be
-    // touched only once it has started).  Waited for just before the first remote store.
-    cluster_arrive_relaxed();
-
-    if (warp == 0) {
-        // ============================ TMA producer ============================
-        if (lane == 0) {
-            pdl_launch_dependents();
-            int pre = 0;
-            if (a.prefetch_w) {
-                pre = min(a.stages, nkb);
-                for (int i = 0; i < pre; ++i) {
-                    mbar_arrive_expect_tx(&full[i], stage_bytes);
-                    tma_load_2d(tiles + i * stage_bytes, &map_w, &full[i], (kb0 + i) * kBlockK, tile * kTileN, kL2EvictFirst);
-                }
-            }
-            pdl_wait();
-            for (int i = 0; i < pre; ++i)
-                tma_load_2d(tiles + i * stage_bytes + kWBytes, &map_x, &full[i], (kb0 + i) * kBlockK, 0, kL2EvictLast);
-            int stage = pre % a.stages;
-            uint32_t phase = (pre == a.stages) ? 1u : 0u;
-            for (int i = pre; i < nkb; ++i) {
-                mbar_wait(&empty[stage], phase ^ 1);
-                unsigned char *ws = tiles + stage * stage_bytes;
-                mbar_arrive_expect_tx(&full[stage], stage_bytes);
-                tma_load_2d(ws, &map_w, &full[stage], (kb0 + i) * kBlockK, tile * kTileN, kL2EvictFirst);
-                tma_load_2d(ws + kWBytes, &map_x, &full[stage], (kb0 + i) * kBlockK, 0, kL2EvictLast);
-                if (++stage == a.stages) {
-                    stage = 0;
-                    phase ^= 1;
-                }
-            }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        // ============================ MMA issuer ============================
-        pdl_wait();
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(kTileN, TP, a.is_bf16 != 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int i = 0; i < nkb; ++i) {
-                mbar_wait(&full[stage], phase);
-                tc_fence_after_sync();
-                const uint32_t wa = smem_u32(tiles + stage * stage_bytes);
-                const uint64_t da = umma_desc_k_sw128(wa), db = umma_desc_k_sw128(wa + kWBytes);
-#pragma unroll
-                for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                    umma_f16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
-                umma_commit(&empty[stage]);
-                if (++stage == a.stages) {
-                    stage = 0;
-                    phase ^= 1;
-                }
-            }
-            umma_commit(&tfull);
-        }
-        __syncwarp();
-    }
-
-    // ============================ epilogue: warps 2..5 hold the accumulator ============================
-    const bool epi = warp >= 2;
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;           // weight row within the tile = output column
-    uint32_t v[TP];                             // this thread's accumulator row: TP fp32 values
-    if (epi) {
-        pdl_wait();
-        mbar_wait(&tfull, 0);
-        tc_fence_after_sync();
-#pragma unroll
-        for (int c = 0; c < TP / 16; ++c) {
-            uint32_t r16[16];
-            tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c * 16, r16);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[c * 16 + j] = r16[j];
-        }
-        tmem_ld_wait();
-    }
-    cluster_wait_acquire();                     // phase 1: every CTA of the cluster is running
-    float *red = reinterpret_cast<float *>(tiles + a.red_off);   // leader: [csize - 1][t_pad][128] fp32
-    if (epi && rank != 0) {
-        const uint32_t base = mapa_shared(smem_u32(red + static_cast<size_t>(rank - 1) * TP * kTileN + row), 0);
-#pragma unroll
-        for (int t = 0; t < TP; ++t) st_shared_cluster_f32(base + t * kTileN * 4, __uint_as_float(v[t]));
-    }
-    cluster_arrive_release();                   // phase 2: the partials are in the leader's shared memory
-    cluster_wait_acquire();
-    if (epi && rank == 0) {
-        const int ncol = tile * kTileN + row;
-        __nv_bfloat16 *yb = static_cast<__nv_bfloat16 *>(a.y);
-        __half *yh = static_cast<__half *>(a.y);
-        if (ncol < a.N) {
-#pragma unroll
-            for (int t = 0; t < TP; ++t) {
-                if (t < a.T) {
-                    float acc = __uint_as_float(v[t]);
-                    for (int r = 0; r + 1 < a.csize; ++r) acc += red[(static_cast<size_t>(r) * TP + t) * kTileN + row];
-                    if (a.is_bf16) yb[static_cast<int64_t>(t) * a.ldy + ncol] = __float2bfloat16_rn(acc);
-                    else yh[static_cast<int64_t>(t) * a.ldy + ncol] = __float2half_rn(acc);
-                }
-            }
-        }
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after_sync();
-        tmem_dealloc(tmem_base, a.tmem_cols);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 struct Map2Key {
     const void *ptr;
     int64_t rows, cols, ld;
@@ -563,85 +406,7 @@ bool make_operand_map(CUtensorMap *out, const void *ptr, int64_t rows, int64_t c
 
 void *g_gemm_trace = nullptr;
 int g_gemm_stage_limit = 0;  // diagnostics (atoma_debug_gemm_stages): 0 = as many as fit
-int g_gemm_algo = 0;         // atoma_debug_gemm_algo: 0 = stream-K (default), 1 = try the cluster variant first
-
-// Cluster variant (experimental): returns 1 if launched, 0 if the shape / device does not qualify
-// (caller continues with stream-K), -1 on error.
-template <int TP>
-int launch_cluster_tp(const CUtensorMap &mw, const CUtensorMap &mx, GemmArgs a, int n_tiles, cudaStream_t stream) {
-    const DeviceInfo &di = current_device_info();
-    const int stage_bytes = kWBytes + TP * 128;
-    const int red_bytes = (a.csize - 1) * TP * kTileN * 4;
-    a.stages = std::min(kMaxStages, (200 * 1024 - red_bytes) / stage_bytes);
-    if (a.stages < 3) return 0;
-    a.red_off = a.stages * stage_bytes;
-    int cols = 32;
-    while (cols < TP) cols <<= 1;
-    a.tmem_cols = cols;
-    const size_t smem = static_cast<size_t>(a.red_off) + red_bytes + 1024;
-    auto kernel = gemm_tn_cluster_kernel<TP>;
-    static thread_local int attr_dev = -1;
-    if (attr_dev != di.ordinal) {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024) != cudaSuccess) {
-            cudaGetLastError();
-            return 0;
-        }
-        attr_dev = di.ordinal;
-    }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(static_cast<unsigned>(n_tiles * a.csize));
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = static_cast<unsigned>(a.csize);
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    // every cluster must be resident at once: a second wave would double the time
-    static thread_local int occ_key = -1, occ_val = 0;
-    const int key = (di.ordinal << 16) | (a.csize << 8) | a.stages;
-    if (occ_key != key) {
-        int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) {
-            cudaGetLastError();
-            n = 0;
-        }
-        occ_key = key;
-        occ_val = n;
-    }
-    if (occ_val < n_tiles) return 0;
-    if (launch_flags() & kLaunchPdl) {
-        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[1].val.programmaticStreamSerializationAllowed = 1;
-        cfg.numAttrs = 2;
-    }
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, mw, mx, a);
-    note_launch();
-    if (e != cudaSuccess) {
-        set_status(static_cast<int>(e), "gemm_tn_cluster_kernel: %s", cudaGetErrorString(e));
-        return -1;
-    }
-    return check_launch("gemm_tn_cluster_kernel") ? 1 : -1;
-}
-
-int try_launch_cluster_gemm(const CUtensorMap &mw, const CUtensorMap &mx, const GemmArgs &a0, cudaStream_t stream) {
-    if (a0.t_chunks != 1 || a0.t_pad > kMaxTPadCluster) return 0;
-    const DeviceInfo &di = current_device_info();
-    const int n_tiles = a0.tiles;
-    GemmArgs a = a0;
-    a.csize = std::min(std::min(4, di.sm_count / std::max(1, n_tiles)), a.kb_per_tile);
-    if (a.csize < 2 || n_tiles * a.csize * 5 < di.sm_count * 4) return 0;   // needs >= 80 % of the SMs busy
-    switch (a.t_pad) {
-        case 16: return launch_cluster_tp<16>(mw, mx, a, n_tiles, stream);
-        case 32: return launch_cluster_tp<32>(mw, mx, a, n_tiles, stream);
-        case 48: return launch_cluster_tp<48>(mw, mx, a, n_tiles, stream);
-        case 64: return launch_cluster_tp<64>(mw, mx, a, n_tiles, stream);
-        default: return 0;
-    }
-}
+int g_gemm_algo = 0;         // atoma_debug_gemm_algo: 0 = decode shapes on the skinny kernel (default), 2 = everything on stream-K
 
 bool launch_stream_gemm(const void *x, const void *w, void *y, int T, int64_t N, int64_t K, int64_t ldx,
                         int64_t ldw, int64_t ldy, bool is_bf16, cudaStream_t stream) {
@@ -675,17 +440,10 @@ bool launch_stream_gemm(const void *x, const void *w, void *y, int T, int64_t N,
     a.ws = reinterpret_cast<float *>(ws);
     a.trace = static_cast<unsigned long long *>(g_gemm_trace);
     a.prefetch_w = ((launch_flags() & (kLaunchPdl | kLaunchConstWeights)) == (kLaunchPdl | kLaunchConstWeights)) ? 1 : 0;
-    a.csize = 1;
-    a.red_off = 0;
 
     CUtensorMap mw, mx;
     if (!make_operand_map(&mw, w, N, K, ldw, kTileN, is_bf16)) return false;
     if (!make_operand_map(&mx, x, T, K, ldx, a.t_pad, is_bf16)) return false;
-
-    if (g_gemm_algo == 1) {
-        const int r = try_launch_cluster_gemm(mw, mx, a, stream);
-        if (r != 0) return r > 0;
-    }
 
     static thread_local int attr_dev = -1;
     if (attr_dev != di.ordinal) {

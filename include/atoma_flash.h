@@ -243,9 +243,8 @@ void atoma_debug_decode_merge(int enable);
 void atoma_debug_gemm_trace(void *device_buf);
 /* Diagnostics: cap the GEMM's shared-memory ring at `stages` stages (0 = as many as fit). */
 void atoma_debug_gemm_stages(int stages);
-/* Diagnostics: 0 (default) = stream-K GEMM; 1 = try the EXPERIMENTAL cluster variant first (one
- * thread-block cluster per weight tile, split reduced through distributed shared memory; decode
- * shapes only; parity-green but not yet tuned — the default path never takes it). */
+/* Diagnostics: 0 (default) = T <= 128 with K % 64 == 0 on the decode-time kernel (gemm_skinny.cu), everything
+ * else on the stream-K kernel; 2 = everything on the stream-K kernel (A/B measurements, regression tests). */
 void atoma_debug_gemm_algo(int algo);
 
 /* 0 = last call on this thread succeeded; otherwise a negative atoma code or a cudaError_t. */

@@ -48,13 +48,6 @@ def main():
             return a.elapsed_time(b) * 1e3 / (reps * nrot)
         t_ours = time_it(lambda i: ops.gemm_bf16_tn(x, ws[i % nrot], out=y))
         t_cluster = None
-        if "--cluster" in sys.argv and T <= 64:   # experimental variant (atoma_debug_gemm_algo)
-            from atoma_infer_b200 import _lib
-            _lib.lib().atoma_debug_gemm_algo(1)
-            try:
-                t_cluster = time_it(lambda i: ops.gemm_bf16_tn(x, ws[i % nrot], out=y))
-            finally:
-                _lib.lib().atoma_debug_gemm_algo(0)
         t_cublas = time_it(lambda i: torch.matmul(x, ws[i % nrot].t(), out=y))
         byts = 2 * (N * K + T * K + T * N)
         flops = 2.0 * T * N * K

@@ -486,3 +486,21 @@ def test_peaky_softmax_range():
     lens = [300, 511, 64]
     out, want, path, is_bf16 = _decode_case(3, 32, 8, 128, 16, 32, lens, torch.bfloat16, seed=13, q_scale=4.0)
     assert_close_16(t2f32(out), want, True, "peaky decode")
+
+
+def test_sliding_window_and_softcap_are_refused_not_silently_ignored():
+    """The reference compiles LOCAL and SOFTCAP out (static_switch.h:7-11) and computes full attention for
+    them; round 1 did the same silently.  A window that would mask something, or a soft cap, now raises."""
+    q = randn_t((1, 64, 4, 64), 1, torch.bfloat16, DEV)
+    k = randn_t((1, 64, 2, 64), 2, torch.bfloat16, DEV)
+    v = randn_t((1, 64, 2, 64), 3, torch.bfloat16, DEV)
+    full = ops.flash_attn(q, k, v, 0.125, causal=True)
+    # a left window longer than the sequence is folded to "none" by the wrapper (csrc/src/lib.rs:250-255): plain causal
+    assert torch.equal(ops.flash_attn_windowed(q, k, v, 0.125, 1000, 0), full)
+    with pytest.raises(ops.AtomaError, match="sliding-window"):
+        ops.flash_attn_windowed(q, k, v, 0.125, 8, 0)
+    with pytest.raises(ops.AtomaError, match="sliding-window"):
+        ops.flash_attn_windowed(q, k, v, 0.125, -1, 4)
+    plan = ops.flash_attn_plan(q, k, v, 0.125, None, 0, softcap=30.0)
+    with pytest.raises(ops.AtomaError, match="soft-capped"):
+        ops._execute(plan, q)

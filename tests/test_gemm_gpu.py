@@ -81,26 +81,3 @@ def test_gemm_exact_small_integers():
     exact = x.double().cpu() @ w.double().cpu().T            # |.| <= 4 * 4096, not all bf16-exact
     want = exact.to(torch.float32).to(torch.bfloat16)
     assert torch.equal(y.cpu(), want)
-
-
-@pytest.mark.skipif(__import__("os").environ.get("ATOMA_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental cluster/DSMEM GEMM variant (opt-in, passed on a B200 at the end of round 1, not "
-                           "yet tuned); set ATOMA_TEST_EXPERIMENTAL=1 to run it")
-@pytest.mark.parametrize("T,N,K", [(32, 6144, 4096), (32, 4096, 4096), (16, 1280, 8192), (1, 3072, 2048),
-                                   (48, 4096, 4096), (64, 6144, 4096), (5, 5000, 4040)])
-def test_gemm_cluster_variant_vs_fp64(T, N, K):
-    """atoma_debug_gemm_algo(1): one cluster per weight tile, split reduced through distributed shared
-    memory.  Same tolerance as the default kernel; deterministic run to run."""
-    from atoma_infer_b200 import _lib
-    x = randn_t((T, K), 1, torch.bfloat16, DEV)
-    w = randn_t((N, K), 2, torch.bfloat16, DEV, scale=K ** -0.5)
-    L = _lib.lib()
-    L.atoma_debug_gemm_algo(1)
-    try:
-        y = ops.gemm_bf16_tn(x, w)
-        y2 = ops.gemm_bf16_tn(x, w)
-        torch.cuda.synchronize()
-    finally:
-        L.atoma_debug_gemm_algo(0)
-    _check(x, w, y, f"cluster gemm T={T} N={N} K={K}")
-    assert torch.equal(y, y2)
