@@ -225,6 +225,8 @@ SIGNATURES = {
     "atoma_debug_skinny_trace": (None, [C.c_void_p]),
     "atoma_debug_skinny_tuning": (None, [C.c_int] * 3),
     "atoma_debug_skinny_mode": (None, [C.c_int] * 2),
+    "atoma_debug_skinny_budget": (None, [C.c_int]),
+    "atoma_debug_step_prefetch": (None, [C.c_int] * 2),
     # atoma_ops.h
     "atoma_flash_attn_plan": (C.c_char_p, [C.POINTER(Tensor)] * 4 + [C.c_float, C.c_int64, C.c_int64, C.c_float,
                                                                     C.c_int, C.POINTER(MhaPlan)]),

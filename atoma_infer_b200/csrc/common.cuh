@@ -54,6 +54,17 @@ enum : int { kLaunchPdl = 1, kLaunchConstWeights = 2, kLaunchStableCache = 4 };
 int launch_flags();
 void set_next_decode_stable_cache(int v);   // per-call form of kLaunchStableCache (thread-local, one-shot)
 int take_next_decode_stable_cache();
+// "What the NEXT kernel of the stream will stream first" (the decode-step executor knows: the next GEMM's
+// weights).  One-shot, thread-local, consumed by the next skinny-GEMM / paged-decode launch on this thread: its
+// producer warps issue L2 prefetches of [ptr, ptr + bytes) once their own last load is in flight, so that HBM
+// keeps streaming through the kernel's tail, the kernel boundary and the next kernel's ramp-up.
+struct NextPrefetch {
+    const void *ptr;
+    long long bytes;
+};
+void set_next_kernel_prefetch(const void *ptr, long long bytes);
+void set_next_kernel_prefetch_off(int off);   // diagnostics: ignore the hints (A/B measurements)
+NextPrefetch take_next_kernel_prefetch();
 void mark_cache_dirty(cudaStream_t stream);   // a cache-maintenance op was enqueued on this stream
 bool take_cache_dirty(cudaStream_t stream);   // ... since the last paged decode launch on it?
 
@@ -100,6 +111,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// L2 prefetch of `bytes` (multiple of 16) at a 16-byte aligned global address: no destination, no completion.
+__device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// [base, base + bytes) is prefetched in 16 KiB pieces; pieces [i0, i1) by the caller.
+constexpr long long kL2PrefetchPiece = 16 * 1024;
+__device__ __forceinline__ long long l2_prefetch_pieces(long long bytes) {
+    return (bytes + kL2PrefetchPiece - 1) / kL2PrefetchPiece;
+}
+__device__ __forceinline__ void l2_prefetch_range(const unsigned char *base, long long bytes, long long i0, long long i1) {
+    for (long long i = i0; i < i1; ++i) {
+        const long long off = i * kL2PrefetchPiece;
+        const long long n = min(kL2PrefetchPiece, bytes - off) & ~15ll;
+        if (n > 0) l2_prefetch_bulk(base + off, static_cast<uint32_t>(n));
+    }
 }
 
 // One lane of the (converged) warp: true in exactly one thread.  Code under `if (elect_one_sync())`

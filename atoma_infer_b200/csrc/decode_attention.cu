@@ -80,6 +80,10 @@ struct DecodeArgs {
     float *ws_ml;    // [cta][2][8 warps][16 rows][2]
     float *ws_o;     // [cta][2][8 warps][16 rows][D]
     unsigned long long *trace;  // diagnostics (atoma_debug_decode_trace): [cta][4] or null
+    // what the next kernel of the stream streams first (o_proj's weights in a decode step): prefetched into L2
+    // by the producer warps once their own last load is in flight, i.e. under this kernel's split-reduction tail
+    const unsigned char *pf_ptr;
+    long long pf_bytes;
 };
 
 __device__ __forceinline__ unsigned long long global_timer_ns() {
@@ -405,6 +409,11 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap map_k,
                 }
             }
             u += n;
+        }
+        if (a.pf_bytes > 0 && lane == 0) {
+            const long long pieces = l2_prefetch_pieces(a.pf_bytes);
+            const int part = cta * kProducerWarps + pw, parts = ncta * kProducerWarps;
+            l2_prefetch_range(a.pf_ptr, a.pf_bytes, pieces * part / parts, pieces * (part + 1) / parts);
         }
         return;
     }
@@ -826,6 +835,9 @@ bool launch_decode(const CUtensorMap &mk, const CUtensorMap &mv, const DecodeArg
     if (attr_dev != di.ordinal) {
         cudaFuncSetAttribute(decode_paged_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(smem));
+        // the same (maximum) carve-out as every other kernel of the decode step: see gemm_skinny.cu
+        cudaFuncSetAttribute(decode_paged_kernel<T, D>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
         attr_dev = di.ordinal;
     }
     cudaError_t e = launch_ex(decode_paged_kernel<T, D>, dim3(a.num_ctas), dim3(kDecodeThreads), smem, stream, mk, mv, a);
@@ -895,6 +907,12 @@ int try_launch_decode_paged(const MhaParams &p, bool is_bf16, int64_t max_units_
     a.ws_ml = reinterpret_cast<float *>(ws + counters_bytes);
     a.ws_o = reinterpret_cast<float *>(ws + counters_bytes + ml_bytes);
     a.trace = static_cast<unsigned long long *>(g_decode_trace);
+    {
+        const NextPrefetch pf = take_next_kernel_prefetch();
+        const bool pf_ok = pf.ptr && pf.bytes >= 16 && (reinterpret_cast<uintptr_t>(pf.ptr) & 15) == 0;
+        a.pf_ptr = pf_ok ? static_cast<const unsigned char *>(pf.ptr) : nullptr;
+        a.pf_bytes = pf_ok ? pf.bytes : 0;
+    }
 
     // K and V views of one [2, NB, bs, Hkv, D] allocation (flash_attention.rs:239-246, 274-275): one
     // tensor map over both, one op per page for K and V together (op size x2 — what decides the

@@ -48,6 +48,18 @@ int launch_flags() { return g_launch_flags.load(std::memory_order_relaxed); }
 namespace {
 thread_local int t_next_stable_cache = 0;
 }
+namespace {
+thread_local NextPrefetch t_next_prefetch = {nullptr, 0};
+std::atomic<int> g_next_prefetch_off{0};
+}
+void set_next_kernel_prefetch(const void *ptr, long long bytes) { t_next_prefetch = NextPrefetch{ptr, ptr ? bytes : 0}; }
+void set_next_kernel_prefetch_off(int off) { g_next_prefetch_off.store(off); }
+NextPrefetch take_next_kernel_prefetch() {
+    NextPrefetch v = t_next_prefetch;
+    t_next_prefetch = NextPrefetch{nullptr, 0};
+    if (g_next_prefetch_off.load(std::memory_order_relaxed)) v = NextPrefetch{nullptr, 0};
+    return v;
+}
 void set_next_decode_stable_cache(int v) { t_next_stable_cache = v; }
 int take_next_decode_stable_cache() {
     const int v = t_next_stable_cache;

@@ -41,11 +41,17 @@ namespace {
 
 constexpr int kSkThreads = 256;             // warps: 0 W producer, 1 MMA, 2-5 epilogue, 6 idle, 7 x producer
 constexpr int kSkMaxStages = 12;
-constexpr int kSkSmemBudget = 200 * 1024;   // ring; + tail slack + 1 KiB alignment < 227 KiB
+constexpr int kSkSmemBudget = 200 * 1024;   // ring of a CTA that owns its SM; + tail slack + 1 KiB alignment < 227 KiB
+// "Half footprint": ring + slack <= half of an SM's shared memory and <= 256 tensor-memory columns, so that TWO
+// CTAs fit on an SM — not for this kernel's own sake (one wave of tiles still gets one CTA per SM) but so that the
+// NEXT kernel of the stream (programmatic dependent launch) becomes resident and streams its weights while this
+// one drains: HBM does not idle across the kernel boundary.
+constexpr int kSkHalfBudget = 100 * 1024;
 // One thread issues only ~5 TMA tensor ops per microsecond whatever their size (measured: round 1's
 // tma_probe; here 0.25 us per stage with two ops per stage from one thread), so a stage is made of FEW,
 // LARGE ops — up to 96 KiB per stage, the weight box split over two issuing warps, x from a third.
 constexpr int kSkStageTarget = 96 * 1024;
+constexpr int kSkDefaultBudget = kSkSmemBudget;
 
 __device__ __forceinline__ unsigned long long sk_timer_ns() {
     unsigned long long t;
@@ -141,11 +147,19 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         tma_prefetch_desc(&map_w);
         tma_prefetch_desc(&map_x);
     }
-    if (warp == 1) tmem_alloc(&tmem_base_smem, a.tmem_cols);
-    tc_fence_before_sync();
+    // The mbarriers are ready once this barrier releases; the tensor-memory allocation (which can block while a
+    // co-resident CTA of the previous kernel still holds its columns) is awaited only by the warps that use it
+    // (named barrier 1), so the producers start streaming W at once.
     __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem_base = tmem_base_smem;
+    if (warp == 1) {
+        tmem_alloc(&tmem_base_smem, a.tmem_cols);
+        tc_fence_before_sync();
+    }
+    if (warp >= 1 && warp <= 5) {
+        named_bar_sync(1, 5 * 32);
+        tc_fence_after_sync();
+    }
+    const uint32_t tmem_base = (warp >= 1 && warp <= 5) ? tmem_base_smem : 0u;
 
     const int my_tiles = (a.tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
     const int total = my_tiles * a.chunks;   // (tile, k chunk) stages this CTA streams
@@ -169,6 +183,15 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         int stage = 0;
         uint32_t phase = 0;
         int n = 0;
+        // this CTA's share of the next kernel's prefetch region (W producer only)
+        long long pf_i = 0, pf_end = 0;
+        int pf_step = 0;
+        if (is_w && a.pf_bytes > 0) {
+            const long long pieces = l2_prefetch_pieces(a.pf_bytes);
+            pf_i = pieces * blockIdx.x / gridDim.x;
+            pf_end = pieces * (blockIdx.x + 1) / gridDim.x;
+            if (a.pf_spread) pf_step = static_cast<int>((pf_end - pf_i + total - 1) / max(total, 1));
+        }
         // no integer division inside the stage loop (a runtime division costs this warp hundreds of
         // cycles — more than a whole stage of MMAs)
         for (int it = 0; it < my_tiles; ++it) {
@@ -202,11 +225,21 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
                     }
                 }
                 __syncwarp();
+                if (pf_step > 0 && pf_i < pf_end) {   // warp-uniform
+                    const long long e = min(pf_end, pf_i + pf_step);
+                    if (elect_one_sync()) l2_prefetch_range(a.pf_ptr, a.pf_bytes, pf_i, e);
+                    __syncwarp();
+                    pf_i = e;
+                }
                 if (++stage == a.stages) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
+        }
+        if (pf_i < pf_end) {   // warp-uniform
+            if (elect_one_sync()) l2_prefetch_range(a.pf_ptr, a.pf_bytes, pf_i, pf_end);
+            __syncwarp();
         }
         if (pre != 0 && n <= pre) pdl_wait();   // everything fitted in the prefetch: still order after the predecessor
         if (a.trace && pre == 0 && is_w && lane == 0) a.trace[blockIdx.x * 4 + 0] = t_start;
@@ -219,8 +252,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         int stage = 0;
         uint32_t phase = 0;
         for (int it = 0; it < my_tiles; ++it) {
-            const int buf = it & 1;
-            mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);   // the epilogue drained this accumulator
+            const int buf = a.nbuf == 2 ? (it & 1) : 0, use = a.nbuf == 2 ? (it >> 1) : it;
+            mbar_wait(&tempty[buf], (use & 1) ^ 1);   // the epilogue drained this accumulator
             tc_fence_after_sync();
             // `nacc` accumulators per tile, used round-robin (diagnostics; 1 by default)
             const uint32_t tmem_d0 = tmem_base + buf * (a.nacc * a.acc_stride);
@@ -285,9 +318,9 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
 
         for (int it = 0; it < my_tiles; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
-            const int buf = it & 1;
+            const int buf = a.nbuf == 2 ? (it & 1) : 0, use = a.nbuf == 2 ? (it >> 1) : it;
             const int g = tile / a.tiles_per_group, p0 = (tile % a.tiles_per_group) * np;
-            mbar_wait(&tfull[buf], (it >> 1) & 1);
+            mbar_wait(&tfull[buf], use & 1);
             tc_fence_after_sync();
             if (a.trace && tid == 64) a.trace[blockIdx.x * 4 + 2] = sk_timer_ns();
             const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * (a.nacc * a.acc_stride);
@@ -472,6 +505,7 @@ int g_sk_stage_limit = 0;
 int g_sk_debug_skip = 0;     // diagnostics (timing experiments only; results are garbage): 1 = no x loads, 2 = no W loads
 int g_sk_w_ops = 1;          // weight ops per stage (1 | 2)
 int g_sk_nacc = 0;           // diagnostics: cap on the independent accumulators per tile (0 = automatic)
+int g_sk_budget_kib = 0;     // diagnostics: ring budget in KiB (0 = default)
 
 // Rows per half per tile (multiple of 8, np * halves <= 256) minimising waves x (tile width + a fixed
 // per-tile cost); ties go to the wider tile (fewer CTAs, fewer x re-reads).
@@ -501,6 +535,9 @@ cudaError_t launch_epi(int epi, dim3 grid, size_t smem, cudaStream_t stream, con
         cudaError_t e = cudaSuccess;
         auto set = [&](auto *k) {
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+            // every kernel of the step asks for the same (maximum) shared-memory carve-out: an SM cannot change
+            // its L1 / shared split while CTAs of the previous kernel are resident
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         };
         set(gemm_skinny_kernel<T, M, kEpiPlain>);
         set(gemm_skinny_kernel<T, M, kEpiRope>);
@@ -525,6 +562,10 @@ void set_skinny_tuning(int np, int kbs, int stages) {
     g_sk_force_np = np;
     g_sk_force_kbs = kbs;
     g_sk_stage_limit = stages;
+}
+void set_skinny_budget(int kib) {
+    set_next_kernel_prefetch_off(kib < 0 ? 1 : 0);   // -1: default budget, next-kernel L2 prefetch off (A/B measurements)
+    g_sk_budget_kib = kib > 0 ? kib : 0;
 }
 void set_skinny_debug(int skip, int w_ops) {
     g_sk_debug_skip = skip & 3;
@@ -556,8 +597,10 @@ bool launch_skinny_gemm(SkinnyArgs a, const void *x, const void *w, int T, int64
     a.tiles_per_group = (J + a.np - 1) / a.np;
     a.tiles = G * a.tiles_per_group;
     const int per_kb = (a.n_tile + a.t_box) * 128;
+    const int budget = g_sk_budget_kib > 0 ? g_sk_budget_kib * 1024 : kSkDefaultBudget;
+    const int stage_target = std::min(kSkStageTarget, budget / 2);
     int kbs = 16;
-    while (kbs > 1 && (kbs * per_kb > kSkStageTarget || kbs > a.kb_total)) kbs >>= 1;
+    while (kbs > 1 && (kbs * per_kb > stage_target || kbs > a.kb_total)) kbs >>= 1;
     if (g_sk_force_kbs > 0) kbs = g_sk_force_kbs;
     a.kbs = kbs;
     a.w_ops = (kbs >= 2 && g_sk_w_ops == 2) ? 2 : 1;   // the weight box of a stage is issued as one or two ops
@@ -567,7 +610,7 @@ bool launch_skinny_gemm(SkinnyArgs a, const void *x, const void *w, int T, int64
     a.w_bytes = kbs * a.n_tile * 128;
     a.x_bytes = kbs * a.t_box * 128;
     a.stage_bytes = a.w_bytes + a.x_bytes;
-    a.stages = std::min(kSkMaxStages, kSkSmemBudget / a.stage_bytes);
+    a.stages = std::min(kSkMaxStages, budget / a.stage_bytes);
     if (g_sk_stage_limit > 0) a.stages = std::min(a.stages, g_sk_stage_limit);
     if (a.stages < 2) {
         set_status(kErrUnsupported, "skinny gemm: stage of %d bytes does not fit", a.stage_bytes);
@@ -578,12 +621,24 @@ bool launch_skinny_gemm(SkinnyArgs a, const void *x, const void *w, int T, int64
     // issuing thread's instruction stream, not the tensor pipe)
     a.nacc = 1;
     if (g_sk_nacc > 1) a.nacc = std::min(g_sk_nacc, a.acc_stride <= 64 ? 4 : (a.acc_stride <= 128 ? 2 : 1));
+    // two accumulator buffers (the epilogue of a tile overlaps the MMAs of the CTA's next tile) when they fit the
+    // CTA's share of tensor memory: all 512 columns for a CTA that owns its SM, 256 for a half-footprint CTA
+    const bool half = budget <= kSkHalfBudget;
+    a.nbuf = (2 * a.nacc * a.acc_stride <= (half ? 256 : 512)) ? 2 : 1;
     int cols = 32;
-    while (cols < 2 * a.nacc * a.acc_stride) cols <<= 1;
+    while (cols < a.nbuf * a.nacc * a.acc_stride) cols <<= 1;
     a.tmem_cols = cols;
     a.is_bf16 = is_bf16 ? 1 : 0;
     a.prefetch_w = ((launch_flags() & (kLaunchPdl | kLaunchConstWeights)) == (kLaunchPdl | kLaunchConstWeights)) ? 1 : 0;
     a.trace = static_cast<unsigned long long *>(g_sk_trace);
+    {
+        const NextPrefetch pf = take_next_kernel_prefetch();
+        const bool ok = pf.ptr && pf.bytes >= 16 && (reinterpret_cast<uintptr_t>(pf.ptr) & 15) == 0;
+        a.pf_ptr = ok ? static_cast<const unsigned char *>(pf.ptr) : nullptr;
+        a.pf_bytes = ok ? pf.bytes : 0;
+        // narrow tiles are bound by the tensor-pipe issue rate, not HBM: the prefetch rides along from the start
+        a.pf_spread = a.n_tile <= 64 ? 1 : 0;
+    }
 
     CUtensorMap mw, mx;
     {
@@ -602,9 +657,10 @@ bool launch_skinny_gemm(SkinnyArgs a, const void *x, const void *w, int T, int64
         const uint32_t box[3] = {64, static_cast<uint32_t>(a.t_box), static_cast<uint32_t>(kbs)};
         if (!make_tiled_map(&mx, x, 3, dims, strides, box, is_bf16)) return false;
     }
-    const int grid = std::min(a.tiles, di.sm_count);
     // ring + the rows an M-row A descriptor reads past the last x slab + alignment slack
     const size_t smem = static_cast<size_t>(a.stages) * a.stage_bytes + a.m * 128 + 1024;
+    const int ctas_per_sm = (half && smem <= 113 * 1024 && a.tmem_cols <= 256) ? 2 : 1;
+    const int grid = std::min(a.tiles, di.sm_count * ctas_per_sm);
     cudaError_t e;
     if (is_bf16) {
         e = a.m == 64 ? launch_epi<__nv_bfloat16, 64>(a.epi, dim3(grid), smem, stream, mw, mx, a)

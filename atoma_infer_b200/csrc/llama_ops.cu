@@ -297,6 +297,24 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const T *__restrict__ logi
 
 inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// The small kernels of the step ask for the same (maximum) shared-memory carve-out as the GEMMs and the decode
+// kernel they run between: an SM cannot change its L1 / shared split while CTAs of a neighbouring kernel are
+// resident, and programmatic dependent launch makes exactly that the normal case.
+void prefer_max_carveout_once() {
+    static thread_local int attr_dev = -1;
+    const DeviceInfo &di = current_device_info();
+    if (attr_dev == di.ordinal) return;
+    auto set = [](auto *k) { cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); };
+    set(add_rmsnorm_kernel<__nv_bfloat16, 1>); set(add_rmsnorm_kernel<__nv_bfloat16, 2>);
+    set(add_rmsnorm_kernel<__nv_bfloat16, 4>); set(add_rmsnorm_kernel<__nv_bfloat16, 8>);
+    set(add_rmsnorm_kernel<__half, 1>); set(add_rmsnorm_kernel<__half, 2>);
+    set(add_rmsnorm_kernel<__half, 4>); set(add_rmsnorm_kernel<__half, 8>);
+    set(embedding_kernel<__nv_bfloat16>); set(embedding_kernel<__half>);
+    set(argmax_kernel<__nv_bfloat16>); set(argmax_kernel<__half>);
+    cudaGetLastError();
+    attr_dev = di.ordinal;
+}
+
 template <typename T>
 cudaError_t launch_norm(const NormArgs &a, int threads, cudaStream_t stream) {
     switch (a.world) {
@@ -347,6 +365,7 @@ bool launch_add_rmsnorm(const void *x, const void *residual, void *residual_out,
     }
     const int nvec = a.hidden / 8;
     int threads = std::min(512, (nvec + 31) / 32 * 32);
+    prefer_max_carveout_once();
     cudaError_t e = dtype == 1 ? launch_norm<__nv_bfloat16>(a, threads, stream) : launch_norm<__half>(a, threads, stream);
     note_launch();
     if (e != cudaSuccess) {
@@ -363,6 +382,7 @@ bool launch_embedding(const uint32_t *tokens, const void *table, void *out, int6
         set_status(kErrInvalidArg, "atoma_embedding: 16-bit dtype, hidden a multiple of 8, 16-byte aligned rows");
         return false;
     }
+    prefer_max_carveout_once();
     cudaError_t e;
     if (dtype == 1)
         e = launch_ex(embedding_kernel<__nv_bfloat16>, dim3(static_cast<unsigned>(T)), dim3(256), 0, stream, tokens,
@@ -387,6 +407,7 @@ bool launch_argmax(const void *logits, int64_t T, int64_t vocab, int64_t ld, uin
         set_status(kErrInvalidArg, "atoma_sample_greedy: 16-bit logits with 16-byte aligned rows");
         return false;
     }
+    prefer_max_carveout_once();
     cudaError_t e;
     if (dtype == 1)
         e = launch_ex(argmax_kernel<__nv_bfloat16>, dim3(static_cast<unsigned>(T)), dim3(1024), 0, stream,

@@ -37,6 +37,20 @@ namespace {
 
 inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// Cross-kernel L2 prefetch of the step (see common.cuh: NextPrefetch).  Every weight-streaming kernel of a layer
+// is told what the NEXT one will stream first; bit i of the mask enables one edge (diagnostics: A/B runs).
+//   1: attention -> Wo    2: o_proj -> Wgate_up    4: gate_up -> Wdown    8: down_proj -> next layer's Wqkv / lm_head
+//  16: qkv -> Wo (instead of 1: the prefetch then sits in L2 through the attention kernel)
+// Default 0 (off): measured on a B200 (profiles/r02_step_prefetch_ab.json) every combination is within +-1 us per layer of
+// "off" — at a kernel boundary the dead time is control latency (CTA hand-over, set-up, descriptor fetch, first
+// HBM round trip), not bandwidth, and an L2 hit shortens only the last of those.
+int g_step_prefetch_mask = 0;
+long long g_step_prefetch_cap = 32ll << 20;   // bytes per edge: ~5 us of HBM time, a quarter of L2
+
+inline void hint(int bit, const void *w, long long bytes) {
+    if (g_step_prefetch_mask & bit) set_next_kernel_prefetch(w, std::min(bytes, g_step_prefetch_cap));
+}
+
 // NVTX range for the lifetime of the object (the reference marks its forward passes with
 // tracing spans — models/src/llama.rs:258, 363, 397; these are the profiler-visible equivalent).
 struct NvtxRange {
@@ -330,6 +344,7 @@ extern "C" void atoma_llama_decode_step(const atoma_llama_model *model, const at
                 return;
         }
         // q, k, v projections + RoPE + cache write  (llama.rs:269-304, flash_attention.rs:361)
+        hint(16, ly.wo, hid * nq * 2);
         if (!qkv_rope_cache(s.normed, ly.wqkv, s.qkv, T, hid, hid, hid, nqkv, H, Hkv, D, b.positions, m.cos, m.sin,
                             m.rot_stride, b.slot_mapping, ly.key_cache, ly.value_cache, m.block_stride, m.block_size, dt,
                             stream))
@@ -362,6 +377,7 @@ extern "C" void atoma_llama_decode_step(const atoma_llama_model *model, const at
         // token being decoded, i.e. rows of each sequence's final page: the decode kernel may stream the
         // older pages before its grid dependency resolves.  A per-call promise, made here where it holds.
         set_next_decode_stable_cache(1);
+        hint(1, ly.wo, hid * nq * 2);
         const int r = try_launch_decode_paged(p, dt == 1, 0, stream);
         if (r != 1) {
             if (r == 0)
@@ -371,6 +387,7 @@ extern "C" void atoma_llama_decode_step(const atoma_llama_model *model, const at
             return;
         }
         // o_proj (+ all-reduce send side)  (llama.rs:311; llama_nccl.rs:139)
+        hint(2, ly.w_gate_up, 2 * m.inter * hid * 2);
         if (world > 1) {
             if (!gemm_tn_push(s.attn, ly.wo, T, hid, nq, nq, nq, m.p2p_regions, m.tp_rank, world, m.p2p_slot_bytes, dt, stream))
                 return;
@@ -385,7 +402,10 @@ extern "C" void atoma_llama_decode_step(const atoma_llama_model *model, const at
                 return;
         }
         // MLP: silu(gate) * up, down  (llama.rs:362-366)
+        hint(4, ly.w_down, hid * m.inter * 2);
         if (!gate_up_silu(s.normed, ly.w_gate_up, s.act, T, m.inter, hid, hid, hid, m.inter, dt, stream)) return;
+        if (l + 1 < m.num_layers) hint(8, m.layers[l + 1].wqkv, nqkv * hid * 2);
+        else if (m.lm_head) hint(8, m.lm_head, m.vocab * hid * 2);
         if (world > 1) {
             if (!gemm_tn_push(s.act, ly.w_down, T, hid, m.inter, m.inter, m.inter, m.p2p_regions, m.tp_rank, world,
                               m.p2p_slot_bytes, dt, stream))
@@ -412,3 +432,8 @@ extern "C" void atoma_llama_decode_step(const atoma_llama_model *model, const at
 extern "C" void atoma_debug_skinny_trace(void *device_buf) { set_skinny_trace(device_buf); }
 extern "C" void atoma_debug_skinny_tuning(int np, int kbs, int stages) { set_skinny_tuning(np, kbs, stages); }
 extern "C" void atoma_debug_skinny_mode(int skip_loads, int w_ops) { set_skinny_debug(skip_loads, w_ops); }
+extern "C" void atoma_debug_skinny_budget(int kib) { set_skinny_budget(kib); }
+extern "C" void atoma_debug_step_prefetch(int mask, int cap_mib) {
+    g_step_prefetch_mask = mask;
+    if (cap_mib > 0) g_step_prefetch_cap = static_cast<long long>(cap_mib) << 20;
+}

@@ -26,9 +26,14 @@ struct SkinnyArgs {
     int tiles_per_group, tiles;
     int w_bytes, x_bytes, stage_bytes;
     int acc_stride, tmem_cols, nacc;   // TMEM columns between accumulators, allocation, independent accumulators per tile
+    int nbuf;                          // accumulator buffers (2: a tile's epilogue overlaps the next tile's MMAs; 1)
     int prefetch_w, is_bf16, epi;
     int debug_skip;                // diagnostics: 1 = skip x loads, 2 = skip W loads (garbage results)
     unsigned long long *trace;     // diagnostics: [cta][4] globaltimer ns, or null
+    // ---- what the next kernel of the stream streams first (L2 prefetch by the W producer warp) ----
+    const unsigned char *pf_ptr;
+    long long pf_bytes;
+    int pf_spread;                 // 1: a few pieces per stage from the start (this kernel leaves HBM headroom); 0: all after the last load
     // ---- output (plain / rope / silu) ----
     void *y;
     int64_t ldy;
@@ -57,5 +62,6 @@ bool launch_skinny_gemm(SkinnyArgs a, const void *x, const void *w, int T, int64
 void set_skinny_trace(void *device_buf);
 void set_skinny_tuning(int np, int kbs, int stages);
 void set_skinny_debug(int skip, int w_ops);
+void set_skinny_budget(int kib);
 
 }  // namespace atoma

@@ -173,6 +173,15 @@ void atoma_debug_skinny_tuning(int np, int kbs, int stages);
 /* Timing experiments only (results are garbage): skip_loads bit 0 = issue no x loads, bit 1 = no W loads;
  * w_ops = 1 | 2 weight TMA ops per stage. */
 void atoma_debug_skinny_mode(int skip_loads, int w_ops);
+/* Shared-memory ring budget of the decode-time GEMM in KiB (0 = default).  <= 100 selects the half-footprint
+ * configuration: two CTAs fit on an SM, so the next kernel of the stream becomes resident and streams its
+ * weights while this one drains (programmatic dependent launch). */
+void atoma_debug_skinny_budget(int kib);
+/* Cross-kernel L2 weight prefetch of atoma_llama_decode_step (each weight-streaming kernel prefetches the start
+ * of what the next one streams while its own tail drains).  mask bits: 1 attention -> Wo, 2 o_proj -> Wgate_up,
+ * 4 gate_up -> Wdown, 8 down_proj -> next Wqkv / lm_head, 16 qkv -> Wo; default 0 (measured: no gain).  cap_mib: bytes per edge
+ * (default 32; 0 keeps the current value). */
+void atoma_debug_step_prefetch(int mask, int cap_mib);
 
 #ifdef __cplusplus
 }

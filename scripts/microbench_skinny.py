@@ -143,6 +143,34 @@ def main():
             sw += bench([s for s in shapes[:4] if s[4] == "plain"], f"np={np_} kbs={kbs} stages={st}")
         L.atoma_debug_skinny_tuning(0, 0, 0)
         res["sweep"] = sw
+    if "--budgets" in sys.argv:
+        # ring budget (KiB): <= 100 = half footprint (two CTAs per SM, cross-kernel overlap under PDL)
+        bd = []
+        for kib in (100, 80, 64):
+            L.atoma_debug_skinny_budget(kib)
+            bd += bench(shapes[:5], f"budget={kib}KiB")
+        L.atoma_debug_skinny_budget(0)
+        # how much can ONE SM pull?  force wide tiles so that only 64 / 32 SMs stream
+        for np_ in (64, 128):
+            L.atoma_debug_skinny_tuning(np_, 0, 0)
+            bd += bench([shapes[1], shapes[3]], f"np={np_} (tiles on {4096 // np_} SMs only)")
+        L.atoma_debug_skinny_tuning(0, 0, 0)
+        res["budgets"] = bd
+    if "--half-ring" in sys.argv:
+        # Is a 100 KiB ring enough in steady state?  Without PDL consecutive launches do not overlap, so the block
+        # scheduler places one CTA per SM (no packing of two CTAs of one launch on an SM): the clean comparison.
+        hr = []
+        ops.set_launch_mode()
+        for kib in (0, 100):
+            L.atoma_debug_skinny_budget(kib)
+            hr += bench(shapes[:5], f"no pdl, budget={kib}KiB")
+        for kbs in (1, 2, 4):
+            L.atoma_debug_skinny_tuning(0, kbs, 0)
+            hr += bench(shapes[:4], f"no pdl, budget=100KiB kbs={kbs}")
+        L.atoma_debug_skinny_tuning(0, 0, 0)
+        L.atoma_debug_skinny_budget(0)
+        ops.set_launch_mode(pdl=True, const_weights=True)
+        res["half_ring"] = hr
     if "--experiments" in sys.argv:
         ex = []
         core = [s for s in shapes[:4] if s[4] == "plain"]

@@ -141,6 +141,13 @@ def _worker(rank, world, port, out_dir):
             rel = (diff.norm() / want.norm()).item()
             ulp = torch.exp2(torch.floor(torch.log2(want.pow(2).mean(dim=-1, keepdim=True).sqrt().clamp_min(2.0 ** -126))) - 7)   # bf16 ulp at the row's rms
             res[tag] = (rel, (diff / ulp).max().item())
+            if not head:   # diagnostics for the assertion message: where the largest ulp distance sits
+                flat = int((diff / ulp).argmax())
+                r_, c_ = divmod(flat, want.shape[1])
+                rms = want.pow(2).mean(dim=-1).sqrt()
+                res[tag + "_where"] = dict(row=r_, col=c_, want=want[r_, c_].item(), got=got[r_, c_].item(),
+                                           row_rms=rms[r_].item(), rms_min=rms.min().item(), rms_max=rms.max().item(),
+                                           len=int(lens[r_]), ulp=ulp[r_].item())
             if head:
                 if rel > 3e-2:
                     bad.append((tag, "rel err", rel))
