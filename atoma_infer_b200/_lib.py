@@ -193,6 +193,8 @@ SIGNATURES = {
     "atoma_debug_allreduce_algo": (None, [C.c_int]),
     "atoma_debug_decode_trace": (None, [C.c_void_p]),
     "atoma_debug_decode_merge": (None, [C.c_int]),
+    "atoma_debug_step_trace": (None, [C.c_void_p, C.c_int]),
+    "atoma_debug_step_trace_names": (C.c_int, [C.c_char_p, C.c_int]),
     "atoma_debug_gemm_trace": (None, [C.c_void_p]),
     "atoma_debug_gemm_stages": (None, [C.c_int]),
     "atoma_debug_gemm_algo": (None, [C.c_int]),

@@ -62,6 +62,11 @@ struct NextPrefetch {
     const void *ptr;
     long long bytes;
 };
+// Step timeline (diagnostics, atoma_debug_step_trace): while a trace buffer is set, every kernel launched through
+// the library gets its own slice of it — kStepTraceU64 words = [cta][8] globaltimer stamps — in launch order.
+constexpr int kStepTraceCtas = 160;
+constexpr int kStepTraceU64 = kStepTraceCtas * 8;
+unsigned long long *next_step_trace_slot(const char *kernel_name);   // null when tracing is off or the buffer is full
 void set_next_kernel_prefetch(const void *ptr, long long bytes);
 void set_next_kernel_prefetch_off(int off);   // diagnostics: ignore the hints (A/B measurements)
 NextPrefetch take_next_kernel_prefetch();

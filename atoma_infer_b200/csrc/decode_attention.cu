@@ -907,6 +907,7 @@ int try_launch_decode_paged(const MhaParams &p, bool is_bf16, int64_t max_units_
     a.ws_ml = reinterpret_cast<float *>(ws + counters_bytes);
     a.ws_o = reinterpret_cast<float *>(ws + counters_bytes + ml_bytes);
     a.trace = static_cast<unsigned long long *>(g_decode_trace);
+    if (!a.trace) a.trace = next_step_trace_slot("decode_paged");
     {
         const NextPrefetch pf = take_next_kernel_prefetch();
         const bool pf_ok = pf.ptr && pf.bytes >= 16 && (reinterpret_cast<uintptr_t>(pf.ptr) & 15) == 0;

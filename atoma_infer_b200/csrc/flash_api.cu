@@ -11,6 +11,7 @@
 #include <atomic>
 #include <cstring>
 #include <mutex>
+#include <string>
 #include <unordered_map>
 #include <vector>
 
@@ -47,6 +48,20 @@ int launch_flags() { return g_launch_flags.load(std::memory_order_relaxed); }
 // step executor, run_mha_stream_flags), consumed by the next paged-decode launch on this thread.
 namespace {
 thread_local int t_next_stable_cache = 0;
+}
+namespace {
+std::mutex g_trace_mu;
+unsigned long long *g_step_trace = nullptr;
+int g_step_trace_cap = 0, g_step_trace_seq = 0;
+std::string g_step_trace_names;
+}
+unsigned long long *next_step_trace_slot(const char *kernel_name) {
+    if (!g_step_trace) return nullptr;
+    std::lock_guard<std::mutex> lock(g_trace_mu);
+    if (!g_step_trace || g_step_trace_seq >= g_step_trace_cap) return nullptr;
+    g_step_trace_names += kernel_name;
+    g_step_trace_names += '\n';
+    return g_step_trace + static_cast<size_t>(g_step_trace_seq++) * kStepTraceU64;
 }
 namespace {
 thread_local NextPrefetch t_next_prefetch = {nullptr, 0};
@@ -368,6 +383,23 @@ extern "C" void atoma_gemm_bf16_tn(const void *x, const void *w, void *y, int64_
 }
 
 extern "C" void atoma_debug_decode_trace(void *device_buf) { set_decode_trace(device_buf); }
+extern "C" void atoma_debug_step_trace(void *device_buf, int max_kernels) {
+    std::lock_guard<std::mutex> lock(g_trace_mu);
+    g_step_trace = static_cast<unsigned long long *>(device_buf);
+    g_step_trace_cap = device_buf ? max_kernels : 0;
+    g_step_trace_seq = 0;
+    if (device_buf) g_step_trace_names.clear();
+}
+extern "C" int atoma_debug_step_trace_names(char *out, int cap) {
+    std::lock_guard<std::mutex> lock(g_trace_mu);
+    const int n = static_cast<int>(g_step_trace_names.size());
+    if (out && cap > 0) {
+        const int m = std::min(n, cap - 1);
+        std::memcpy(out, g_step_trace_names.data(), m);
+        out[m] = 0;
+    }
+    return n;
+}
 extern "C" void atoma_debug_gemm_trace(void *device_buf) { set_gemm_trace(device_buf); }
 extern "C" void atoma_debug_decode_merge(int enable) { set_decode_merge(enable); }
 extern "C" void atoma_debug_gemm_stages(int stages) { set_gemm_stage_limit(stages); }

@@ -180,6 +180,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         // previous kernel drains; x (its output) only after the grid dependency has resolved.
         const int pre = (is_w && a.prefetch_w) ? min(a.stages, total) : 0;
         if (pre == 0) pdl_wait();
+        if (a.trace && !is_w && lane == 0) a.trace[blockIdx.x * 8 + 6] = sk_timer_ns();   // x: grid dependency resolved
         int stage = 0;
         uint32_t phase = 0;
         int n = 0;
@@ -200,10 +201,11 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
             for (int ch = 0; ch < a.chunks; ++ch, ++n) {
                 if (n == pre && pre != 0) {
                     pdl_wait();
-                    if (a.trace && lane == 0) a.trace[blockIdx.x * 4 + 0] = t_start;
+                    if (a.trace && lane == 0) a.trace[blockIdx.x * 8 + 0] = t_start;
                 }
                 mbar_wait(&empty[stage], phase ^ 1);   // passes at once during the first trip round the ring
                 unsigned char *dst = ring + stage * a.stage_bytes;
+                if (a.trace && is_w && lane == 0 && (n == 0 || n == total - 1)) a.trace[blockIdx.x * 8 + (n == 0 ? 4 : 5)] = sk_timer_ns();
                 if (elect_one_sync()) {
                     // W is read exactly once by exactly one CTA: evict-first.  x is re-read by every CTA: keep it.
                     if (is_w) {
@@ -242,7 +244,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
             __syncwarp();
         }
         if (pre != 0 && n <= pre) pdl_wait();   // everything fitted in the prefetch: still order after the predecessor
-        if (a.trace && pre == 0 && is_w && lane == 0) a.trace[blockIdx.x * 4 + 0] = t_start;
+        if (a.trace && pre == 0 && is_w && lane == 0) a.trace[blockIdx.x * 8 + 0] = t_start;
     } else if (warp == 1) {
         // ============================ MMA issuer ============================
         pdl_wait();
@@ -261,7 +263,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
             for (int ch = 0; ch < a.chunks; ++ch) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after_sync();
-                if (a.trace && it == 0 && ch == 0 && lane == 0) a.trace[blockIdx.x * 4 + 1] = sk_timer_ns();
+                if (a.trace && it == 0 && ch == 0 && lane == 0) a.trace[blockIdx.x * 8 + 1] = sk_timer_ns();
+                if (a.trace && it == my_tiles - 1 && ch == a.chunks - 1 && lane == 0) a.trace[blockIdx.x * 8 + 7] = sk_timer_ns();
                 const uint32_t base = ring_u32 + stage * a.stage_bytes;
                 const int nkb = min(a.kbs, a.kb_total - ch * a.kbs);   // k blocks past K are zero-filled: skip
                 if (elect_one_sync()) {
@@ -322,7 +325,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
             const int g = tile / a.tiles_per_group, p0 = (tile % a.tiles_per_group) * np;
             mbar_wait(&tfull[buf], use & 1);
             tc_fence_after_sync();
-            if (a.trace && tid == 64) a.trace[blockIdx.x * 4 + 2] = sk_timer_ns();
+            if (a.trace && tid == 64) a.trace[blockIdx.x * 8 + 2] = sk_timer_ns();
             const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * (a.nacc * a.acc_stride);
             // 8 consecutive columns of the tile: the sum of the nacc partial accumulators (fixed order)
             auto load8 = [&](int col, uint32_t (&v)[8]) {
@@ -435,7 +438,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
 
     tc_fence_before_sync();
     __syncthreads();
-    if (a.trace && tid == 0) a.trace[blockIdx.x * 4 + 3] = sk_timer_ns();
+    if (a.trace && tid == 0) a.trace[blockIdx.x * 8 + 3] = sk_timer_ns();
     if (warp == 1) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, a.tmem_cols);
@@ -631,6 +634,8 @@ bool launch_skinny_gemm(SkinnyArgs a, const void *x, const void *w, int T, int64
     a.is_bf16 = is_bf16 ? 1 : 0;
     a.prefetch_w = ((launch_flags() & (kLaunchPdl | kLaunchConstWeights)) == (kLaunchPdl | kLaunchConstWeights)) ? 1 : 0;
     a.trace = static_cast<unsigned long long *>(g_sk_trace);
+    if (!a.trace) a.trace = next_step_trace_slot(a.epi == kEpiRope ? "gemm qkv+rope" : a.epi == kEpiSilu ? "gemm gate_up+silu" :
+                                                 a.epi == kEpiPush ? "gemm push" : "gemm");
     {
         const NextPrefetch pf = take_next_kernel_prefetch();
         const bool ok = pf.ptr && pf.bytes >= 16 && (reinterpret_cast<uintptr_t>(pf.ptr) & 15) == 0;

@@ -89,6 +89,7 @@ struct NormArgs {
     int64_t recv_offset, slot_stride, recv_stride, plane_bytes;
     int world;
     unsigned long long timeout_ns;
+    unsigned long long *trace;   // diagnostics (step timeline): [cta][8] = {-, start, dependency resolved, end}
 };
 
 // One CTA per token row; thread t owns the 16-byte vectors t, t + blockDim, ...
@@ -96,8 +97,10 @@ template <typename T, int W>
 __global__ void __launch_bounds__(512) add_rmsnorm_kernel(const NormArgs a) {
     __shared__ float red[32];
     __shared__ uint32_t s_state[2];
+    if (a.trace && threadIdx.x == 0) a.trace[blockIdx.x * 8 + 1] = ops_timer_ns();
     pdl_launch_dependents();
     pdl_wait();
+    if (a.trace && threadIdx.x == 0) a.trace[blockIdx.x * 8 + 2] = ops_timer_ns();
     const int row = blockIdx.x, nvec = a.hidden / 8;
     uint32_t *state = reinterpret_cast<uint32_t *>(a.region);
     uint32_t e = 0;
@@ -196,6 +199,7 @@ __global__ void __launch_bounds__(512) add_rmsnorm_kernel(const NormArgs a) {
             *reinterpret_cast<uint4 *>(static_cast<T *>(a.normed) + static_cast<int64_t>(row) * a.ldn + v * 8) = pack8f<T>(o);
         }
     }
+    if (a.trace && threadIdx.x == 0) a.trace[blockIdx.x * 8 + 3] = ops_timer_ns();
     if (W > 1) {
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -366,6 +370,7 @@ bool launch_add_rmsnorm(const void *x, const void *residual, void *residual_out,
     const int nvec = a.hidden / 8;
     int threads = std::min(512, (nvec + 31) / 32 * 32);
     prefer_max_carveout_once();
+    a.trace = a.T <= kStepTraceCtas ? next_step_trace_slot(a.world > 1 ? "add_rmsnorm recv" : "add_rmsnorm") : nullptr;
     cudaError_t e = dtype == 1 ? launch_norm<__nv_bfloat16>(a, threads, stream) : launch_norm<__half>(a, threads, stream);
     note_launch();
     if (e != cudaSuccess) {

@@ -239,6 +239,12 @@ void atoma_debug_decode_trace(void *device_buf);
 /* Diagnostics: 0 = the decode kernel always uses separate K and V tensor maps (two ops per page);
  * 1 (default) = one map and one op for K and V when they are views of one allocation. */
 void atoma_debug_decode_merge(int enable);
+/* Step timeline: while device_buf (max_kernels x 1280 u64, zeroed by the caller) is set, every GEMM, paged-decode
+ * and add+RMSNorm launch writes per-CTA globaltimer stamps into its own 1280-word slice, in launch order;
+ * atoma_debug_step_trace_names copies the '\n'-separated kernel labels of the slices (returns their total length).
+ * Pass NULL to stop.  Launch eagerly (not from a graph captured earlier) while tracing. */
+void atoma_debug_step_trace(void *device_buf, int max_kernels);
+int atoma_debug_step_trace_names(char *out, int cap);
 /* Same for the projection GEMM: {start, first operand tile landed, last accumulator complete, end}. */
 void atoma_debug_gemm_trace(void *device_buf);
 /* Diagnostics: cap the GEMM's shared-memory ring at `stages` stages (0 = as many as fit). */

@@ -165,9 +165,10 @@ int64_t atoma_llama_decode_scratch_bytes(const atoma_llama_model *model, int64_t
 void atoma_llama_decode_step(const atoma_llama_model *model, const atoma_decode_batch *batch,
                              atoma_stream_t stream);
 
-/* Diagnostics for the decode-time GEMM: per-CTA timestamps {start, first stage landed, accumulator
- * complete, end} (globaltimer ns) at device_buf[4*cta..]; tile width / k blocks per stage / ring depth
- * overrides (0 = automatic). */
+/* Diagnostics for the decode-time GEMM: per-CTA timestamps (globaltimer ns) at device_buf[8*cta..]: {0 start,
+ * 1 first stage landed, 2 first accumulator complete, 3 end, 4 first / 5 last weight load issued, 6 x producer's
+ * grid dependency resolved, 7 last stage landed}; tile width / k blocks per stage / ring depth overrides
+ * (0 = automatic). */
 void atoma_debug_skinny_trace(void *device_buf);
 void atoma_debug_skinny_tuning(int np, int kbs, int stages);
 /* Timing experiments only (results are garbage): skip_loads bit 0 = issue no x loads, bit 1 = no W loads;

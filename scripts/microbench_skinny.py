@@ -186,7 +186,7 @@ def main():
         for (name, T, N, K, kind) in core:
             w = (torch.randn((N, K), device=DEV) * K ** -0.5).to(BF)
             x = torch.randn((T, K), device=DEV).to(BF)
-            tr = torch.zeros((148 * 4,), dtype=torch.int64, device=DEV)
+            tr = torch.zeros((148 * 8,), dtype=torch.int64, device=DEV)
             ops.gemm_tn(x, w)
             big = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
             big.zero_()   # flush L2
@@ -195,7 +195,7 @@ def main():
             ops.gemm_tn(x, w)
             torch.cuda.synchronize()
             L.atoma_debug_skinny_trace(None)
-            t = tr.view(148, 4).cpu()
+            t = tr.view(148, 8).cpu()
             t = t[t[:, 3] > 0]
             t0 = t[:, 0].min()
             d = (t - t0).float() / 1e3

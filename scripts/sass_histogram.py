@@ -24,7 +24,8 @@ def main():
         m = re.match(r"\s*Function : (\S+)", line)
         if m:
             name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
-            name = re.sub(r"\(.*", "", name).replace("atoma::(anonymous namespace)::", "")
+            name = name.replace("(anonymous namespace)::", "")
+            name = re.sub(r"\(.*", "", name).replace("void ", "").replace("atoma::", "")
             cur = kernels.setdefault(name, collections.Counter())
             continue
         m = re.match(r"\s*/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
