@@ -229,6 +229,9 @@ SIGNATURES = {
     "atoma_debug_skinny_mode": (None, [C.c_int] * 2),
     "atoma_debug_skinny_budget": (None, [C.c_int]),
     "atoma_debug_step_prefetch": (None, [C.c_int] * 2),
+    "atoma_debug_step_fusion": (None, [C.c_int]),
+    "atoma_gemm_tn_add_rmsnorm": (None, [C.c_void_p] * 3 + [C.c_int64] * 6 + [C.c_void_p] * 4 + [C.c_int64] * 3 +
+                                  [C.c_float, C.c_uint32, C.c_void_p]),
     # atoma_ops.h
     "atoma_flash_attn_plan": (C.c_char_p, [C.POINTER(Tensor)] * 4 + [C.c_float, C.c_int64, C.c_int64, C.c_float,
                                                                     C.c_int, C.POINTER(MhaPlan)]),

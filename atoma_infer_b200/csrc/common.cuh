@@ -43,7 +43,7 @@ const DeviceInfo &current_device_info();
 // Library-owned scratch, one per (device, stream, tag); grows monotonically, zero-initialised
 // when (re)allocated.  Used for the decode kernel's split partials + arrival counters and for the
 // device copy of a swap mapping.
-enum : int { kWorkspaceDecode = 0, kWorkspaceSwapMap = 1, kWorkspaceGemm = 2, kWorkspaceGemmCounters = 3, kWorkspaceTags = 4 };
+enum : int { kWorkspaceDecode = 0, kWorkspaceSwapMap = 1, kWorkspaceGemm = 2, kWorkspaceGemmCounters = 3, kWorkspaceSkinnyTail = 4, kWorkspaceTags = 5 };
 void *get_workspace(cudaStream_t stream, size_t bytes, int tag);
 
 // Launch mode (process-wide, atoma_set_launch_mode): programmatic dependent launch between this
@@ -133,6 +133,12 @@ __device__ __forceinline__ void l2_prefetch_range(const unsigned char *base, lon
         const long long n = min(kL2PrefetchPiece, bytes - off) & ~15ll;
         if (n > 0) l2_prefetch_bulk(base + off, static_cast<uint32_t>(n));
     }
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
 // One lane of the (converged) warp: true in exactly one thread.  Code under `if (elect_one_sync())`

@@ -130,6 +130,9 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     unsigned char *ring = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     __shared__ __align__(8) uint64_t full[kSkMaxStages], empty[kSkMaxStages], tfull[2], tempty[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ int s_ticket;
+    __shared__ uint32_t s_tail_state[2];
+    __shared__ float s_red[32];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned long long t_start = a.trace ? sk_timer_ns() : 0ull;
@@ -174,7 +177,10 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         // warp 0: the weight op(s) of every stage; warp 7: the x op.  Each arrives on the stage's full
         // barrier with its own byte count.
         const bool is_w = warp == 0;
-        if (is_w) pdl_launch_dependents();
+        // Release the dependent grid: at once, or (trigger_late) only when this CTA issues its last weight load —
+        // a dependent grid that sits in the hardware queue for tens of microseconds waiting for SMs was measured
+        // to be placed several microseconds late once they free up (scripts/trace_step.py).
+        if (is_w && !a.trigger_late) pdl_launch_dependents();
         const int w_op_bytes = a.w_bytes / a.w_ops;
         // Under programmatic dependent launch with immutable weights the ring is filled with W while the
         // previous kernel drains; x (its output) only after the grid dependency has resolved.
@@ -205,6 +211,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
                 }
                 mbar_wait(&empty[stage], phase ^ 1);   // passes at once during the first trip round the ring
                 unsigned char *dst = ring + stage * a.stage_bytes;
+                if (is_w && a.trigger_late && n == max(total - a.trigger_late, 0)) pdl_launch_dependents();
                 if (a.trace && is_w && lane == 0 && (n == 0 || n == total - 1)) a.trace[blockIdx.x * 8 + (n == 0 ? 4 : 5)] = sk_timer_ns();
                 if (elect_one_sync()) {
                     // W is read exactly once by exactly one CTA: evict-first.  x is re-read by every CTA: keep it.
@@ -443,6 +450,62 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, a.tmem_cols);
     }
+
+    if ((EPI == kEpiPlain || EPI == kEpiPush) && a.norm_tail) {
+        // ============ fused add + RMSNorm of the finished rows, by the CTAs that finish last ============
+        // Every thread's output stores (or peer pushes) are ordered before this CTA's arrival.  Nothing below
+        // can deadlock: a waiting CTA waits only for CTAs of this grid, which never wait for it.
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_ticket = static_cast<int>(atomicAdd(&a.tail_sync[0], 1u));
+        __syncthreads();
+        const int grid = static_cast<int>(gridDim.x), nn = min(a.norm.T, grid);
+        const int j = s_ticket - (grid - nn);
+        if (j < 0) return;
+        uint32_t *state = reinterpret_cast<uint32_t *>(a.norm.region);
+        if (tid == 0) {
+            while (ld_acquire_gpu_u32(&a.tail_sync[0]) < static_cast<uint32_t>(grid)) __nanosleep(64);
+            if (EPI == kEpiPush) {
+                s_tail_state[0] = *reinterpret_cast<volatile uint32_t *>(&state[0]);
+                s_tail_state[1] = *reinterpret_cast<volatile uint32_t *>(&state[2]);
+            }
+        }
+        __syncthreads();
+        __threadfence();
+        uint32_t e = 0;
+        bool skip = false, failed = false;
+        if (EPI == kEpiPush) {
+            e = s_tail_state[0] + 1;           // this all-reduce's epoch (the one the epilogue pushed with)
+            skip = s_tail_state[1] != 0;       // a peer failed to arrive earlier: do not wait for it again
+        }
+        if (!skip) {
+            for (int row = j; row < a.norm.T; row += nn) {
+                if (EPI == kEpiPush) {
+                    switch (a.norm.world) {
+                        case 2: failed |= add_rmsnorm_row<T, 2>(a.norm, row, e, s_red); break;
+                        case 4: failed |= add_rmsnorm_row<T, 4>(a.norm, row, e, s_red); break;
+                        default: failed |= add_rmsnorm_row<T, 8>(a.norm, row, e, s_red); break;
+                    }
+                } else {
+                    add_rmsnorm_row<T, 1>(a.norm, row, 0u, s_red);
+                }
+                __syncthreads();   // s_red is reused by the next row
+            }
+        }
+        if (tid == 0) {
+            if (EPI == kEpiPush && failed) atomicExch(&state[2], 1u);   // error word: a peer never arrived
+            __threadfence();
+            if (atomicAdd(&a.tail_sync[1], 1u) == static_cast<uint32_t>(nn - 1)) {
+                // last norm CTA: counters back to zero for the next launch; the next all-reduce sees the next epoch
+                a.tail_sync[0] = 0;
+                a.tail_sync[1] = 0;
+                if (EPI == kEpiPush) {
+                    __threadfence();
+                    state[0] = e;
+                }
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -509,6 +572,8 @@ int g_sk_debug_skip = 0;     // diagnostics (timing experiments only; results ar
 int g_sk_w_ops = 1;          // weight ops per stage (1 | 2)
 int g_sk_nacc = 0;           // diagnostics: cap on the independent accumulators per tile (0 = automatic)
 int g_sk_budget_kib = 0;     // diagnostics: ring budget in KiB (0 = default)
+int g_sk_trigger_late = 0;   // diagnostics: release the dependent grid N stages before the last weight load (0 = at kernel start)
+int g_sk_single_buf = 1;     // one accumulator buffer for single-tile CTAs (diagnostics: skip_loads bit 3 turns it off)
 
 // Rows per half per tile (multiple of 8, np * halves <= 256) minimising waves x (tile width + a fixed
 // per-tile cost); ties go to the wider tile (fewer CTAs, fewer x re-reads).
@@ -572,6 +637,8 @@ void set_skinny_budget(int kib) {
 }
 void set_skinny_debug(int skip, int w_ops) {
     g_sk_debug_skip = skip & 3;
+    g_sk_single_buf = (skip & 8) ? 0 : 1;
+    g_sk_trigger_late = (skip >> 8) & 0xff;   // bits 8-15
     g_sk_nacc = (skip >> 4) & 7;          // bits 4-6: accumulator cap (1, 2, 4; 0 = automatic)
     g_sk_w_ops = w_ops == 2 ? 2 : 1;
 }
@@ -608,6 +675,7 @@ bool launch_skinny_gemm(SkinnyArgs a, const void *x, const void *w, int T, int64
     a.kbs = kbs;
     a.w_ops = (kbs >= 2 && g_sk_w_ops == 2) ? 2 : 1;   // the weight box of a stage is issued as one or two ops
     a.debug_skip = g_sk_debug_skip;
+    a.trigger_late = g_sk_trigger_late;
     a.wkb = kbs / a.w_ops;
     a.chunks = (a.kb_total + kbs - 1) / kbs;
     a.w_bytes = kbs * a.n_tile * 128;
@@ -628,6 +696,8 @@ bool launch_skinny_gemm(SkinnyArgs a, const void *x, const void *w, int T, int64
     // CTA's share of tensor memory: all 512 columns for a CTA that owns its SM, 256 for a half-footprint CTA
     const bool half = budget <= kSkHalfBudget;
     a.nbuf = (2 * a.nacc * a.acc_stride <= (half ? 256 : 512)) ? 2 : 1;
+    // a CTA that owns a single tile never overlaps an epilogue with a next tile: one buffer, half the columns
+    if (g_sk_single_buf && a.tiles <= di.sm_count) a.nbuf = 1;
     int cols = 32;
     while (cols < a.nbuf * a.nacc * a.acc_stride) cols <<= 1;
     a.tmem_cols = cols;
@@ -635,7 +705,8 @@ bool launch_skinny_gemm(SkinnyArgs a, const void *x, const void *w, int T, int64
     a.prefetch_w = ((launch_flags() & (kLaunchPdl | kLaunchConstWeights)) == (kLaunchPdl | kLaunchConstWeights)) ? 1 : 0;
     a.trace = static_cast<unsigned long long *>(g_sk_trace);
     if (!a.trace) a.trace = next_step_trace_slot(a.epi == kEpiRope ? "gemm qkv+rope" : a.epi == kEpiSilu ? "gemm gate_up+silu" :
-                                                 a.epi == kEpiPush ? "gemm push" : "gemm");
+                                                 a.epi == kEpiPush ? (a.norm_tail ? "gemm push+norm" : "gemm push") :
+                                                 (a.norm_tail ? "gemm+norm" : "gemm"));
     {
         const NextPrefetch pf = take_next_kernel_prefetch();
         const bool ok = pf.ptr && pf.bytes >= 16 && (reinterpret_cast<uintptr_t>(pf.ptr) & 15) == 0;
@@ -643,6 +714,16 @@ bool launch_skinny_gemm(SkinnyArgs a, const void *x, const void *w, int T, int64
         a.pf_bytes = ok ? pf.bytes : 0;
         // narrow tiles are bound by the tensor-pipe issue rate, not HBM: the prefetch rides along from the start
         a.pf_spread = a.n_tile <= 64 ? 1 : 0;
+    }
+
+    if (a.norm_tail) {
+        if ((a.epi != kEpiPlain && a.epi != kEpiPush) || a.norm.hidden > 8 * kSkThreads * kNormMaxVec || a.norm.T != T) {
+            set_status(kErrInvalidArg, "skinny gemm: the fused add+RMSNorm tail needs a plain / push epilogue, hidden <= %d and "
+                                       "one norm row per output row", 8 * kSkThreads * kNormMaxVec);
+            return false;
+        }
+        a.tail_sync = static_cast<uint32_t *>(get_workspace(stream, 256, kWorkspaceSkinnyTail));   // zero-initialised, self-resetting
+        if (!a.tail_sync) return false;
     }
 
     CUtensorMap mw, mx;

@@ -19,6 +19,7 @@
 //   * models/src/multi_gpu.rs:141-179 AllReduce::cuda_fwd: ncclAllReduce(sum) of the [T, hidden] bf16
 //     partial projection; result in bf16.
 #include "common.cuh"
+#include "norm_row.cuh"
 
 #include "atoma_flash.h"
 
@@ -27,72 +28,11 @@
 namespace atoma {
 namespace {
 
-constexpr int kNormMaxVec = 4;   // 16-byte vectors per thread: hidden <= 8 * 512 * 4
+using namespace normrow;
 
-template <typename T>
-__device__ __forceinline__ void unpack8f(const uint4 &v, float (&f)[8]) {
-    const T *p = reinterpret_cast<const T *>(&v);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = static_cast<float>(p[i]);
-}
-template <typename T>
-__device__ __forceinline__ uint4 pack8f(const float (&f)[8]) {
-    uint4 o;
-    o.x = pack2<T>(f[0], f[1]);
-    o.y = pack2<T>(f[2], f[3]);
-    o.z = pack2<T>(f[4], f[5]);
-    o.w = pack2<T>(f[6], f[7]);
-    return o;
-}
-template <typename T>
-__device__ __forceinline__ float round_to(float f) {
-    return static_cast<float>(static_cast<T>(f));
-}
+__device__ __forceinline__ unsigned long long ops_timer_ns() { return timer_ns(); }
 
-__device__ __forceinline__ float block_sum(float v, float *red) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    float s = 0.f;
-    for (int i = 0; i < nw; ++i) s += red[i];   // fixed order: every thread gets the same bits
-    return s;
-}
-
-__device__ __forceinline__ uint4 ld_volatile_v4(const void *p) {
-    uint4 v;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p)
-                 : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long ops_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
-    return t;
-}
-
-struct NormArgs {
-    const void *x;         // [T, hidden] addend (projection output) or null
-    const void *residual;  // [T, hidden] or null (first layer: h = x)
-    void *residual_out;    // [T, hidden] h = x + residual (may alias residual or x), or null
-    const void *weight;    // [hidden]
-    void *normed;          // [T, hidden] rmsnorm(h) * weight, or null (only the add is wanted)
-    int64_t ldx, ldr, ldro, ldn;
-    int hidden, T;
-    float eps;
-    // receive side of the tensor-parallel all-reduce (world > 1): x is the rank-order fp32 sum of the
-    // addends every rank pushed into recv[slot][r] of this rank's region, rounded to the io type
-    unsigned char *region;   // local region
-    int64_t recv_offset, slot_stride, recv_stride, plane_bytes;
-    int world;
-    unsigned long long timeout_ns;
-    unsigned long long *trace;   // diagnostics (step timeline): [cta][8] = {-, start, dependency resolved, end}
-};
-
-// One CTA per token row; thread t owns the 16-byte vectors t, t + blockDim, ...
+// One CTA per token row (norm_row.cuh).
 template <typename T, int W>
 __global__ void __launch_bounds__(512) add_rmsnorm_kernel(const NormArgs a) {
     __shared__ float red[32];
@@ -101,10 +41,9 @@ __global__ void __launch_bounds__(512) add_rmsnorm_kernel(const NormArgs a) {
     pdl_launch_dependents();
     pdl_wait();
     if (a.trace && threadIdx.x == 0) a.trace[blockIdx.x * 8 + 2] = ops_timer_ns();
-    const int row = blockIdx.x, nvec = a.hidden / 8;
+    const int row = blockIdx.x;
     uint32_t *state = reinterpret_cast<uint32_t *>(a.region);
     uint32_t e = 0;
-    bool failed = false;
     if (W > 1) {
         if (threadIdx.x == 0) {
             s_state[0] = *reinterpret_cast<volatile uint32_t *>(&state[0]);
@@ -114,93 +53,10 @@ __global__ void __launch_bounds__(512) add_rmsnorm_kernel(const NormArgs a) {
         e = s_state[0] + 1;               // this all-reduce's epoch
         if (s_state[1] != 0) return;      // a peer failed to arrive earlier: do not wait for it again (block-uniform)
     }
-    float h[kNormMaxVec][8];
-    float ss = 0.f;
-#pragma unroll
-    for (int u = 0; u < kNormMaxVec; ++u) {
-        const int v = threadIdx.x + u * blockDim.x;
-        if (v >= nvec) break;
-        float x[8];
-        if (W > 1) {
-            // poll the W addends of vector i (8-byte units {data, epoch}); add in rank order, round once
-            const int64_t i = static_cast<int64_t>(row) * nvec + v;
-            const unsigned char *src = a.region + a.recv_offset + (e & 1u) * a.slot_stride + i * 16;
-            uint4 lo[W > 1 ? W : 1], hi[W > 1 ? W : 1];
-            bool done[W > 1 ? W : 1];
-#pragma unroll
-            for (int r = 0; r < W; ++r) done[r] = false;
-            const unsigned long long t0 = ops_timer_ns();
-            for (int spin = 0;; ++spin) {
-                bool all = true;
-#pragma unroll
-                for (int r = 0; r < W; ++r) {
-                    if (!done[r]) {
-                        lo[r] = ld_volatile_v4(src + r * a.recv_stride);
-                        hi[r] = ld_volatile_v4(src + r * a.recv_stride + a.plane_bytes);
-                        done[r] = lo[r].y == e && lo[r].w == e && hi[r].y == e && hi[r].w == e;
-                        all = all && done[r];
-                    }
-                }
-                if (all) break;
-                if ((spin & 63) == 63 && ops_timer_ns() - t0 > a.timeout_ns) {
-                    failed = true;
-                    break;
-                }
-            }
-            if (failed) break;
-            float acc[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-            for (int r = 0; r < W; ++r) {
-                float f[8];
-                unpack8f<T>(make_uint4(lo[r].x, lo[r].z, hi[r].x, hi[r].z), f);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] += f[j];
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = round_to<T>(acc[j]);   // the all-reduce result is in the io type
-        } else if (a.x) {
-            unpack8f<T>(*reinterpret_cast<const uint4 *>(static_cast<const T *>(a.x) + static_cast<int64_t>(row) * a.ldx + v * 8), x);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = 0.f;
-        }
-        if (a.residual) {
-            float r[8];
-            unpack8f<T>(*reinterpret_cast<const uint4 *>(static_cast<const T *>(a.residual) + static_cast<int64_t>(row) * a.ldr + v * 8), r);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = round_to<T>(x[j] + r[j]);   // the add is in the model dtype
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            h[u][j] = x[j];
-            ss += x[j] * x[j];
-        }
-        if (a.residual_out)
-            *reinterpret_cast<uint4 *>(static_cast<T *>(a.residual_out) + static_cast<int64_t>(row) * a.ldro + v * 8) = pack8f<T>(x);
-    }
-    int any_failed = 0;
-    if (W > 1) {
-        any_failed = __syncthreads_or(failed ? 1 : 0);
-        if (any_failed && threadIdx.x == 0) atomicExch(&state[2], 1u);   // error word: a peer never arrived
-    }
-    const float total = block_sum(ss, red);
-    if (a.normed && !any_failed) {
-        const float scale = rsqrtf(total / static_cast<float>(a.hidden) + a.eps);
-#pragma unroll
-        for (int u = 0; u < kNormMaxVec; ++u) {
-            const int v = threadIdx.x + u * blockDim.x;
-            if (v >= nvec) break;
-            float w[8], o[8];
-            unpack8f<T>(*reinterpret_cast<const uint4 *>(static_cast<const T *>(a.weight) + v * 8), w);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = scale * h[u][j] * w[j];
-            *reinterpret_cast<uint4 *>(static_cast<T *>(a.normed) + static_cast<int64_t>(row) * a.ldn + v * 8) = pack8f<T>(o);
-        }
-    }
+    const bool failed = add_rmsnorm_row<T, W>(a, row, e, red);
     if (a.trace && threadIdx.x == 0) a.trace[blockIdx.x * 8 + 3] = ops_timer_ns();
     if (W > 1) {
+        if (failed && threadIdx.x == 0) atomicExch(&state[2], 1u);   // error word: a peer never arrived
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
@@ -341,6 +197,16 @@ void p2p_layout(int64_t slot_bytes, int64_t *recv_offset, int64_t *slot_stride, 
     *recv_offset = 4096 + 2 * s;
 }
 
+void norm_args_set_p2p(NormArgs &a, void *p2p_region, int64_t p2p_slot_bytes, int world) {
+    a.world = world > 1 ? world : 1;
+    a.region = static_cast<unsigned char *>(p2p_region);
+    if (a.world > 1) {
+        p2p_layout(p2p_slot_bytes, &a.recv_offset, &a.slot_stride, &a.recv_stride);
+        a.plane_bytes = static_cast<int64_t>(a.T) * a.hidden * 2;
+        a.timeout_ns = 30000000000ull;
+    }
+}
+
 bool launch_add_rmsnorm(const void *x, const void *residual, void *residual_out, const void *weight, void *normed,
                         int64_t T, int64_t hidden, int64_t ldx, int64_t ldr, int64_t ldro, int64_t ldn, float eps,
                         uint32_t dtype, void *p2p_region, int64_t p2p_slot_bytes, int world, cudaStream_t stream) {
@@ -360,15 +226,11 @@ bool launch_add_rmsnorm(const void *x, const void *residual, void *residual_out,
     a.hidden = static_cast<int>(hidden);
     a.T = static_cast<int>(T);
     a.eps = eps;
-    a.world = world > 1 ? world : 1;
-    a.region = static_cast<unsigned char *>(p2p_region);
-    if (a.world > 1) {
-        p2p_layout(p2p_slot_bytes, &a.recv_offset, &a.slot_stride, &a.recv_stride);
-        a.plane_bytes = static_cast<int64_t>(T) * hidden * 2;
-        a.timeout_ns = 30000000000ull;
-    }
+    norm_args_set_p2p(a, p2p_region, p2p_slot_bytes, world);
     const int nvec = a.hidden / 8;
-    int threads = std::min(512, (nvec + 31) / 32 * 32);
+    // 256 threads whenever they can hold the row (hidden <= 8192): the same thread -> vector assignment and the same
+    // reduction order as the fused tail of the row-parallel projections (gemm_skinny.cu), hence the same bits
+    int threads = std::min(nvec > 256 * kNormMaxVec ? 512 : 256, (nvec + 31) / 32 * 32);
     prefer_max_carveout_once();
     a.trace = a.T <= kStepTraceCtas ? next_step_trace_slot(a.world > 1 ? "add_rmsnorm recv" : "add_rmsnorm") : nullptr;
     cudaError_t e = dtype == 1 ? launch_norm<__nv_bfloat16>(a, threads, stream) : launch_norm<__half>(a, threads, stream);

@@ -60,8 +60,9 @@ struct NvtxRange {
     NvtxRange &operator=(const NvtxRange &) = delete;
 };
 
+// `tail` (optional): residual add + RMSNorm of y's rows fused into the kernel's tail (norm_row.cuh); tail->x is set here.
 bool gemm_tn(const void *x, const void *w, void *y, int64_t T, int64_t N, int64_t K, int64_t ldx, int64_t ldw,
-             int64_t ldy, uint32_t dtype, cudaStream_t stream) {
+             int64_t ldy, uint32_t dtype, cudaStream_t stream, const NormArgs *tail = nullptr) {
     if (T <= 0 || N <= 0) return true;
     if (dtype > 1 || K <= 0 || !x || !w || !y || !al16(x) || !al16(w) || ldx % 8 || ldw % 8 || ldx < K || ldw < K ||
         ldy < N) {
@@ -77,8 +78,19 @@ bool gemm_tn(const void *x, const void *w, void *y, int64_t T, int64_t N, int64_
         a.epi = kEpiPlain;
         a.y = y;
         a.ldy = ldy;
+        if (tail) {
+            a.norm_tail = 1;
+            a.norm = *tail;
+            a.norm.x = y;
+            a.norm.ldx = ldy;
+        }
         return launch_skinny_gemm(a, x, w, static_cast<int>(T), K, ldx, ldw, 1, static_cast<int>(N), 1, 0, 0, dtype == 1,
                                   stream);
+    }
+    if (tail) {
+        set_status(kErrUnsupported, "atoma_gemm_tn_add_rmsnorm: needs T <= 128 and K %% 64 == 0 (T=%lld K=%lld)",
+                   static_cast<long long>(T), static_cast<long long>(K));
+        return false;
     }
     if (dtype != 1) {
         set_status(kErrUnsupported, "atoma_gemm_tn: f16 needs T <= 128 and K %% 64 == 0 (T=%lld K=%lld)",
@@ -161,7 +173,8 @@ bool gate_up_silu(const void *x, const void *w, void *y, int64_t T, int64_t inte
 }
 
 bool gemm_tn_push(const void *x, const void *w, int64_t T, int64_t N, int64_t K, int64_t ldx, int64_t ldw,
-                  void *const *regions, int rank, int world, int64_t slot_bytes, uint32_t dtype, cudaStream_t stream) {
+                  void *const *regions, int rank, int world, int64_t slot_bytes, uint32_t dtype, cudaStream_t stream,
+                  const NormArgs *tail = nullptr) {
     if (T <= 0 || N <= 0) return true;
     if (dtype > 1 || !regions || world < 2 || world > 8 || (world & (world - 1)) || rank < 0 || rank >= world || N % 8 ||
         T * N * 2 > slot_bytes || !x || !w || !al16(x) || !al16(w) || ldx % 8 || ldw % 8 || ldx < K || ldw < K) {
@@ -184,9 +197,35 @@ bool gemm_tn_push(const void *x, const void *w, int64_t T, int64_t N, int64_t K,
     a.push_plane_bytes = T * N * 2;
     a.push_rank = rank;
     a.push_world = world;
+    if (tail) {   // receive side (the all-reduce's sum + residual + RMSNorm) in the same kernel
+        a.norm_tail = 1;
+        a.norm = *tail;
+        a.norm.x = nullptr;
+        norm_args_set_p2p(a.norm, regions[rank], slot_bytes, world);
+    }
     return launch_skinny_gemm(a, x, w, static_cast<int>(T), K, ldx, ldw, 1, static_cast<int>(N), 1, 0, 0, dtype == 1,
                               stream);
 }
+
+// Arguments of a fused tail: h = y + residual -> residual_out; normed = rmsnorm(h) * weight.
+NormArgs norm_tail_args(const void *residual, void *residual_out, const void *weight, void *normed, int64_t T,
+                        int64_t hidden, int64_t ldr, int64_t ldro, int64_t ldn, float eps) {
+    NormArgs n{};
+    n.residual = residual; n.residual_out = residual_out; n.weight = weight; n.normed = normed;
+    n.ldr = ldr; n.ldro = ldro; n.ldn = ldn;
+    n.hidden = static_cast<int>(hidden);
+    n.T = static_cast<int>(T);
+    n.eps = eps;
+    n.world = 1;
+    return n;
+}
+
+// 1: the add+RMSNorm after o_proj and after down_proj run in the tail of those GEMMs (5 launches per layer);
+// 0 (default): as separate kernels (7 launches per layer) — atoma_debug_step_fusion.  Measured on a B200
+// (profiles/r02_step_fusion_ab.json): the fused tail is 1.5 us per norm SLOWER (190.2 vs 187.1 us per layer at tp = 1,
+// 66.5 vs 64.2 for a tp8 shard): the norm CTAs must first wait for the slowest CTA of the grid, whereas the separate
+// norm kernel is already resident (PDL) and its 32 CTAs start the moment the GEMM's grid completes.  Same bits.
+int g_step_norm_tail = 0;
 
 struct Scratch {
     char *resid, *normed, *qkv, *attn, *proj, *act, *logits;
@@ -326,6 +365,11 @@ extern "C" void atoma_llama_decode_step(const atoma_llama_model *model, const at
     } else {
         resid_in = b.hidden_in;
     }
+    // The add + RMSNorm that follows each row-parallel projection runs in that GEMM's tail (gemm_skinny.cu) unless
+    // switched off or the row does not fit the GEMM's CTA: 5 launches per layer instead of 7.
+    const bool fuse = g_step_norm_tail && hid <= 8 * 256 * kNormMaxVec && skinny_gemm_supported(T, nq, nq, nq) &&
+                      skinny_gemm_supported(T, m.inter, m.inter, m.inter);
+    void *final_normed = b.hidden_out ? b.hidden_out : s.normed;
     for (int64_t l = 0; l < m.num_layers; ++l) {
         const atoma_llama_layer &ly = m.layers[l];
         NvtxRange layer_range("block");
@@ -334,6 +378,8 @@ extern "C" void atoma_llama_decode_step(const atoma_llama_model *model, const at
             if (!launch_add_rmsnorm(nullptr, resid_in, s.resid, ly.rms_attn, s.normed, T, hid, hid, hid, hid, hid, m.rms_eps,
                                     dt, nullptr, 0, 1, stream))
                 return;
+        } else if (fuse) {
+            // done in the tail of the previous layer's down_proj
         } else if (world > 1) {
             if (!launch_add_rmsnorm(nullptr, s.resid, s.resid, ly.rms_attn, s.normed, T, hid, hid, hid, hid, hid, m.rms_eps,
                                     dt, m.p2p_regions[m.tp_rank], m.p2p_slot_bytes, world, stream))
@@ -388,7 +434,17 @@ extern "C" void atoma_llama_decode_step(const atoma_llama_model *model, const at
         }
         // o_proj (+ all-reduce send side)  (llama.rs:311; llama_nccl.rs:139)
         hint(2, ly.w_gate_up, 2 * m.inter * hid * 2);
-        if (world > 1) {
+        // x = attn + residual; rms_2(x)  (llama.rs:401-407)
+        const NormArgs tail_mlp = norm_tail_args(s.resid, s.resid, ly.rms_mlp, s.normed, T, hid, hid, hid, hid, m.rms_eps);
+        if (fuse) {
+            if (world > 1) {
+                if (!gemm_tn_push(s.attn, ly.wo, T, hid, nq, nq, nq, m.p2p_regions, m.tp_rank, world, m.p2p_slot_bytes, dt, stream,
+                                  &tail_mlp))
+                    return;
+            } else {
+                if (!gemm_tn(s.attn, ly.wo, s.proj, T, hid, nq, nq, nq, hid, dt, stream, &tail_mlp)) return;
+            }
+        } else if (world > 1) {
             if (!gemm_tn_push(s.attn, ly.wo, T, hid, nq, nq, nq, m.p2p_regions, m.tp_rank, world, m.p2p_slot_bytes, dt, stream))
                 return;
             if (!launch_add_rmsnorm(nullptr, s.resid, s.resid, ly.rms_mlp, s.normed, T, hid, hid, hid, hid, hid, m.rms_eps, dt,
@@ -406,7 +462,19 @@ extern "C" void atoma_llama_decode_step(const atoma_llama_model *model, const at
         if (!gate_up_silu(s.normed, ly.w_gate_up, s.act, T, m.inter, hid, hid, hid, m.inter, dt, stream)) return;
         if (l + 1 < m.num_layers) hint(8, m.layers[l + 1].wqkv, nqkv * hid * 2);
         else if (m.lm_head) hint(8, m.lm_head, m.vocab * hid * 2);
-        if (world > 1) {
+        if (fuse) {
+            // x = mlp + residual, then the NEXT block's rms_1 — or ln_f after the last block  (llama.rs:408, 399, 474)
+            const bool last = l + 1 == m.num_layers;
+            const NormArgs tail_next = norm_tail_args(s.resid, last ? nullptr : s.resid, last ? m.norm_f : m.layers[l + 1].rms_attn,
+                                                      last ? final_normed : s.normed, T, hid, hid, hid, hid, m.rms_eps);
+            if (world > 1) {
+                if (!gemm_tn_push(s.act, ly.w_down, T, hid, m.inter, m.inter, m.inter, m.p2p_regions, m.tp_rank, world,
+                                  m.p2p_slot_bytes, dt, stream, &tail_next))
+                    return;
+            } else {
+                if (!gemm_tn(s.act, ly.w_down, s.proj, T, hid, m.inter, m.inter, m.inter, hid, dt, stream, &tail_next)) return;
+            }
+        } else if (world > 1) {
             if (!gemm_tn_push(s.act, ly.w_down, T, hid, m.inter, m.inter, m.inter, m.p2p_regions, m.tp_rank, world,
                               m.p2p_slot_bytes, dt, stream))
                 return;
@@ -415,8 +483,8 @@ extern "C" void atoma_llama_decode_step(const atoma_llama_model *model, const at
         }
     }
     // x = mlp + residual; ln_f  (llama.rs:408, 474)
-    void *final_normed = b.hidden_out ? b.hidden_out : s.normed;
-    if (!launch_add_rmsnorm(world > 1 ? nullptr : s.proj, s.resid, nullptr, m.norm_f, final_normed, T, hid, hid, hid, hid, hid,
+    if (!fuse &&
+        !launch_add_rmsnorm(world > 1 ? nullptr : s.proj, s.resid, nullptr, m.norm_f, final_normed, T, hid, hid, hid, hid, hid,
                             m.rms_eps, dt, world > 1 ? m.p2p_regions[m.tp_rank] : nullptr, m.p2p_slot_bytes, world, stream))
         return;
     if (!m.lm_head) return;
@@ -433,6 +501,22 @@ extern "C" void atoma_debug_skinny_trace(void *device_buf) { set_skinny_trace(de
 extern "C" void atoma_debug_skinny_tuning(int np, int kbs, int stages) { set_skinny_tuning(np, kbs, stages); }
 extern "C" void atoma_debug_skinny_mode(int skip_loads, int w_ops) { set_skinny_debug(skip_loads, w_ops); }
 extern "C" void atoma_debug_skinny_budget(int kib) { set_skinny_budget(kib); }
+extern "C" void atoma_debug_step_fusion(int norm_tail) { g_step_norm_tail = norm_tail ? 1 : 0; }
+
+extern "C" void atoma_gemm_tn_add_rmsnorm(const void *x, const void *w, void *y, int64_t T, int64_t N, int64_t K, int64_t ldx,
+                                          int64_t ldw, int64_t ldy, const void *residual, void *residual_out,
+                                          const void *weight, void *normed, int64_t ldr, int64_t ldro, int64_t ldn, float eps,
+                                          uint32_t dtype, atoma_stream_t stream) {
+    clear_status();
+    if (N % 8 || N > 8 * 256 * kNormMaxVec || (normed && !weight) || !al16(residual) || !al16(residual_out) || !al16(weight) ||
+        !al16(normed) || ldr % 8 || ldro % 8 || ldn % 8 || ldy % 8 || !al16(y)) {
+        set_status(kErrInvalidArg, "atoma_gemm_tn_add_rmsnorm: N a multiple of 8 and <= %d, 16-byte aligned pointers and row strides",
+                   8 * 256 * kNormMaxVec);
+        return;
+    }
+    const NormArgs tail = norm_tail_args(residual, residual_out, weight, normed, T, N, ldr, ldro, ldn, eps);
+    gemm_tn(x, w, y, T, N, K, ldx, ldw, ldy, dtype, static_cast<cudaStream_t>(stream), &tail);
+}
 extern "C" void atoma_debug_step_prefetch(int mask, int cap_mib) {
     g_step_prefetch_mask = mask;
     if (cap_mib > 0) g_step_prefetch_cap = static_cast<long long>(cap_mib) << 20;

@@ -6,6 +6,8 @@
 
 #include <cstdint>
 
+#include "norm_row.cuh"
+
 namespace atoma {
 
 enum : int {
@@ -29,6 +31,7 @@ struct SkinnyArgs {
     int nbuf;                          // accumulator buffers (2: a tile's epilogue overlaps the next tile's MMAs; 1)
     int prefetch_w, is_bf16, epi;
     int debug_skip;                // diagnostics: 1 = skip x loads, 2 = skip W loads (garbage results)
+    int trigger_late;              // 0: release the dependent grid at kernel start; N: N stages before this CTA's last weight load
     unsigned long long *trace;     // diagnostics: [cta][4] globaltimer ns, or null
     // ---- what the next kernel of the stream streams first (L2 prefetch by the W producer warp) ----
     const unsigned char *pf_ptr;
@@ -53,6 +56,12 @@ struct SkinnyArgs {
     int64_t push_recv_stride;      // bytes between recv[s][r] and recv[s][r + 1]
     int64_t push_plane_bytes;      // bytes between the two 16-byte planes of a vector
     int push_rank, push_world;
+    // ---- fused add + RMSNorm tail (plain / push epilogues of the row-parallel projections o_proj, down_proj):
+    // the min(T, grid) CTAs that finish LAST wait until every CTA's tile is stored (or pushed) and then run the
+    // residual add + RMSNorm of the token rows (norm_row.cuh) — the separate norm launch disappears ----
+    int norm_tail;
+    uint32_t *tail_sync;           // [2], zero between launches: CTAs finished, norm CTAs finished
+    NormArgs norm;                 // norm.x = this GEMM's y (plain) or null (push: the receive buffers)
 };
 
 bool skinny_gemm_supported(int64_t T, int64_t K, int64_t ldx, int64_t ldw);

@@ -423,6 +423,26 @@ def add_rmsnorm(x, residual, weight, eps: float, residual_out=None, normed=None)
     return residual_out, normed
 
 
+def gemm_tn_add_rmsnorm(x, w, residual, weight, eps: float, out=None, residual_out=None, normed=None):
+    """y = x w^T; h = y + residual; normed = rmsnorm(h) * weight — one kernel (llama.rs:311 + 401-407).  Returns
+    (y, h, normed); bit-identical to gemm_tn followed by add_rmsnorm."""
+    T, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((T, N), dtype=x.dtype, device=x.device)
+    if residual_out is None:
+        residual_out = torch.empty((T, N), dtype=x.dtype, device=x.device)
+    if normed is None and weight is not None:
+        normed = torch.empty((T, N), dtype=x.dtype, device=x.device)
+    p = lambda t: t.data_ptr() if t is not None else None
+    ld = lambda t: t.stride(0) if t is not None else N
+    _lib.lib().atoma_gemm_tn_add_rmsnorm(x.data_ptr(), w.data_ptr(), out.data_ptr(), T, N, K, x.stride(0), w.stride(0),
+                                         out.stride(0), p(residual), p(residual_out), p(weight), p(normed), ld(residual),
+                                         ld(residual_out), ld(normed), eps, _dt(x), _stream())
+    _raise_on_status()
+    return out, residual_out, normed
+
+
 def embedding(tokens, table, out=None) -> torch.Tensor:
     """table[tokens] (llama.rs:470); tokens: int32/uint32 bit patterns [T]."""
     T = tokens.numel()

@@ -73,6 +73,17 @@ void atoma_add_rmsnorm(const void *x, const void *residual, void *residual_out, 
                        void *normed, int64_t T, int64_t hidden, int64_t ldx, int64_t ldr, int64_t ldro,
                        int64_t ldn, float eps, uint32_t dtype, atoma_stream_t stream);
 
+/*
+ * Row-parallel projection + residual add + RMSNorm, ONE kernel (llama.rs:311 + 401-407; 365 + 408 + 399):
+ *   y = x w^T (as atoma_gemm_tn; T <= 128, K % 64 == 0), then h = y + residual -> residual_out and
+ *   normed = rmsnorm(h) * weight exactly as atoma_add_rmsnorm computes them (bit-identical to the two calls).  The
+ *   CTAs of the GEMM that finish last normalise the rows: no second launch.  N = the normalised width (<= 8192).
+ */
+void atoma_gemm_tn_add_rmsnorm(const void *x, const void *w, void *y, int64_t T, int64_t N, int64_t K, int64_t ldx,
+                               int64_t ldw, int64_t ldy, const void *residual, void *residual_out, const void *weight,
+                               void *normed, int64_t ldr, int64_t ldro, int64_t ldn, float eps, uint32_t dtype,
+                               atoma_stream_t stream);
+
 /* out[t, :] = table[tokens[t], :] (llama.rs:470 `wte.forward`). */
 void atoma_embedding(const uint32_t *tokens, const void *table, void *out, int64_t T, int64_t hidden,
                      int64_t vocab, int64_t ld_table, int64_t ldo, uint32_t dtype, atoma_stream_t stream);
@@ -183,6 +194,10 @@ void atoma_debug_skinny_budget(int kib);
  * 4 gate_up -> Wdown, 8 down_proj -> next Wqkv / lm_head, 16 qkv -> Wo; default 0 (measured: no gain).  cap_mib: bytes per edge
  * (default 32; 0 keeps the current value). */
 void atoma_debug_step_prefetch(int mask, int cap_mib);
+/* atoma_llama_decode_step: 1 = the add+RMSNorm after o_proj / down_proj runs in the tail of those GEMMs
+ * (5 launches per layer, under tensor parallelism the receive side of the all-reduce included); 0 (default) =
+ * separate kernels (7 launches per layer; measured 1.5 us per norm faster).  Same bits either way. */
+void atoma_debug_step_fusion(int norm_tail);
 
 #ifdef __cplusplus
 }

@@ -43,7 +43,15 @@ def main():
         L.atoma_debug_skinny_budget(0)
         L.atoma_debug_skinny_tuning(0, 0, 0)
         L.atoma_debug_step_prefetch(0, 32)
-        if v.startswith("pf"):      # pf<mask>[_<cap MiB>]
+        L.atoma_debug_step_fusion(0)
+        L.atoma_debug_skinny_mode(0, 1)
+        if v == "dbuf":             # two accumulator buffers even for single-tile CTAs (the round-2 default before)
+            L.atoma_debug_skinny_mode(8, 1)
+        elif v.startswith("late"):    # late<N>: GEMMs release their dependents N stages before their last weight load
+            L.atoma_debug_skinny_mode(int(v[4:]) << 8, 1)
+        elif v.startswith("fuse"):
+            L.atoma_debug_step_fusion(int(v[4:]))
+        elif v.startswith("pf"):      # pf<mask>[_<cap MiB>]
             mk, _, cap = v[2:].partition("_")
             L.atoma_debug_step_prefetch(int(mk), int(cap) if cap else 32)
         elif v.startswith("b"):
@@ -79,6 +87,8 @@ def main():
     L.atoma_debug_skinny_budget(0)
     L.atoma_debug_skinny_tuning(0, 0, 0)
     L.atoma_debug_step_prefetch(0, 32)
+    L.atoma_debug_step_fusion(0)
+    L.atoma_debug_skinny_mode(0, 1)
     ops.set_launch_mode()
     (ROOT / args.out).parent.mkdir(exist_ok=True)
     (ROOT / args.out).write_text(json.dumps(res, indent=1))

@@ -256,6 +256,63 @@ def test_add_rmsnorm(T, hidden, dtype):
     assert torch.equal(r2, h) and torch.equal(n2, n)
 
 
+@pytest.mark.parametrize("T,N,K,dtype", [(32, 4096, 4096, BF), (1, 2048, 512, BF), (7, 1024, 1344, F16), (64, 4096, 1792, BF),
+                                          (128, 8192, 1024, BF), (100, 264, 192, BF), (16, 8192, 3584, F16)])
+def test_gemm_tn_add_rmsnorm_is_bit_identical_to_the_two_calls(T, N, K, dtype):
+    """The fused tail (the CTAs of the GEMM that finish last normalise its rows) against gemm_tn + add_rmsnorm:
+    same bits for y, h and normed; its arrival counters reset themselves (repeated launches, graph replay); h may
+    alias the residual (what the step does)."""
+    x = randn_t((T, K), 51, dtype, DEV)
+    w = randn_t((N, K), 52, dtype, DEV, scale=K ** -0.5)
+    r = randn_t((T, N), 53, dtype, DEV, scale=2.0)
+    nw = (1.0 + 0.1 * randn_t((N,), 54, torch.float32, DEV)).to(dtype)
+    y0 = ops.gemm_tn(x, w)
+    h0, n0 = ops.add_rmsnorm(y0, r, nw, 1e-5)
+    for it in range(3):
+        y, h, n = ops.gemm_tn_add_rmsnorm(x, w, r, nw, 1e-5)
+        torch.cuda.synchronize()
+        assert torch.equal(y, y0) and torch.equal(h, h0) and torch.equal(n, n0), f"launch {it}"
+    r2, n2 = r.clone(), torch.empty_like(r)
+    ops.gemm_tn_add_rmsnorm(x, w, r2, nw, 1e-5, residual_out=r2, normed=n2)      # in-place residual stream
+    assert torch.equal(r2, h0) and torch.equal(n2, n0)
+    # no norm weight: only the add;  no residual: h = y
+    _, h3, n3 = ops.gemm_tn_add_rmsnorm(x, w, r, None, 1e-5)
+    assert n3 is None and torch.equal(h3, h0)
+    _, h4, n4 = ops.gemm_tn_add_rmsnorm(x, w, None, nw, 1e-5)
+    h5, n5 = ops.add_rmsnorm(y0, None, nw, 1e-5)
+    assert torch.equal(h4, h5) and torch.equal(n4, n5)
+    # graph replay, programmatic dependent launch on, two fused GEMMs back to back
+    ops.set_launch_mode(pdl=True, const_weights=True)
+    try:
+        ya, ha, na = torch.empty_like(y0), torch.empty_like(y0), torch.empty_like(y0)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            ops.gemm_tn_add_rmsnorm(x, w, r, nw, 1e-5, out=ya, residual_out=ha, normed=na)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            ops.gemm_tn_add_rmsnorm(x, w, r, nw, 1e-5, out=ya, residual_out=ha, normed=na)
+            ops.gemm_tn_add_rmsnorm(x, w, r, nw, 1e-5, out=ya, residual_out=ha, normed=na)
+        for _ in range(3):
+            ya.zero_(); ha.zero_(); na.zero_()
+            g.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(ya, y0) and torch.equal(ha, h0) and torch.equal(na, n0)
+    finally:
+        ops.set_launch_mode()
+
+
+def test_gemm_tn_add_rmsnorm_errors():
+    x = randn_t((4, 128), 1, BF, DEV)
+    w = randn_t((16392, 128), 2, BF, DEV)
+    with pytest.raises(ops.AtomaError, match="gemm_tn_add_rmsnorm"):
+        ops.gemm_tn_add_rmsnorm(x, w, None, None, 1e-5)            # wider than a GEMM CTA can normalise
+    xw = randn_t((130, 128), 3, BF, DEV)
+    with pytest.raises(ops.AtomaError, match="T <= 128"):
+        ops.gemm_tn_add_rmsnorm(xw, randn_t((256, 128), 4, BF, DEV), None, None, 1e-5)
+
+
 def test_embedding_and_greedy_sampling():
     vocab, hidden, T = 1000, 264, 9
     table = randn_t((vocab, hidden), 51, BF, DEV)
@@ -436,6 +493,31 @@ def test_decode_step_pdl_modes_are_bit_identical():
         assert torch.equal(lg, outs[0][0])
         for a, b in zip(caches, outs[0][1]):
             assert torch.equal(a, b)
+
+
+def test_decode_step_norm_fusion_on_and_off_are_bit_identical():
+    """atoma_debug_step_fusion: the add+RMSNorm in the tail of o_proj / down_proj (5 launches per layer) against the
+    separate kernels (7 per layer)."""
+    from atoma_infer_b200 import _lib
+    L = _lib.lib()
+    T = 9
+    outs = []
+    for fused in (1, 0):
+        cfg, shard, kv, bt, lens, pos, slots, tokens = _small_setup(T, seed=17)
+        L.atoma_debug_step_fusion(fused)
+        try:
+            step = DecodeStep(shard, kv, max_batch=T, want_logits=True, want_hidden=True)
+            step.bind(tokens, pos, slots, bt, lens)
+            n = step.launches_per_step()
+            assert n == (2 + 5 * cfg.num_hidden_layers + 2 if fused else 1 + 7 * cfg.num_hidden_layers + 3)
+            step.launch()
+            torch.cuda.synchronize()
+            outs.append((step.logits[:T].clone(), step.hidden_out[:T].clone(), step.next_tokens[:T].clone(), [c.clone() for c in kv]))
+        finally:
+            L.atoma_debug_step_fusion(0)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    for a, b in zip(outs[0][3], outs[1][3]):
+        assert torch.equal(a, b)
 
 
 def test_decode_step_argument_errors():
