@@ -134,7 +134,7 @@ class LlamaModel(C.Structure):
                  ("embed", C.c_void_p), ("norm_f", C.c_void_p), ("lm_head", C.c_void_p),
                  ("cos", C.c_void_p), ("sin", C.c_void_p), ("layers", C.POINTER(LlamaLayer)),
                  ("tp_rank", C.c_int32), ("tp_world", C.c_int32), ("p2p_regions", C.POINTER(C.c_void_p)),
-                 ("p2p_slot_bytes", C.c_int64)])
+                 ("p2p_slot_bytes", C.c_int64), ("lm_head_rows", C.c_int64), ("lm_head_row0", C.c_int64)])
 
 
 class DecodeBatch(C.Structure):
@@ -230,6 +230,8 @@ SIGNATURES = {
     "atoma_debug_skinny_budget": (None, [C.c_int]),
     "atoma_debug_step_prefetch": (None, [C.c_int] * 2),
     "atoma_debug_step_fusion": (None, [C.c_int]),
+    "atoma_sample_greedy_tp": (None, [C.c_void_p] + [C.c_int64] * 4 + [C.c_uint32, C.c_void_p, C.c_void_p,
+                                                                        C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64, C.c_void_p]),
     "atoma_gemm_tn_add_rmsnorm": (None, [C.c_void_p] * 3 + [C.c_int64] * 6 + [C.c_void_p] * 4 + [C.c_int64] * 3 +
                                   [C.c_float, C.c_uint32, C.c_void_p]),
     # atoma_ops.h

@@ -321,6 +321,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         }
         uint32_t epoch = 0;
         int slot_sel = 0;
+        unsigned char *stg = ring + a.stages * a.stage_bytes + M * 128;   // push epilogue: [t_box][np] staging behind the ring
         if (EPI == kEpiPush) {
             epoch = a.push_state[0] + 1;   // this all-reduce's epoch (advanced by the receive-side kernel)
             slot_sel = static_cast<int>(epoch & 1u);
@@ -364,20 +365,44 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
                         if (EPI == kEpiPlain) {
                             store8<T>(y + j0, o, J - j0, y_vec);
                         } else {
-                            // tensor parallel: this rank's addend of vector i goes to recv[slot][rank] of EVERY
-                            // rank (own included) as two 16-byte stores {w0,e,w1,e} {w2,e,w3,e}
-                            const int64_t i16 = (static_cast<int64_t>(row) * J + j0) >> 3;
-                            const int64_t off = a.push_recv_offset + slot_sel * a.push_slot_stride +
-                                                a.push_rank * a.push_recv_stride + i16 * 16;
-#pragma unroll 1
-                            for (int d = 0; d < a.push_world; ++d) {
-                                const int r = (a.push_rank + d) % a.push_world;
-                                unsigned char *dst = a.push_region[r] + off;
-                                st_relaxed_sys_v4(dst, o.x, epoch, o.y, epoch);
-                                st_relaxed_sys_v4(dst + a.push_plane_bytes, o.z, epoch, o.w, epoch);
-                            }
+                            // tensor parallel: stage the tile in shared memory; pushed below, coalesced
+                            *reinterpret_cast<uint4 *>(stg + (static_cast<size_t>(row) * np + c + 8 * u) * sizeof(T)) = o;
                         }
                     }
+                }
+                if (EPI == kEpiPush) {
+                    // This rank's addend goes to recv[slot][rank] of EVERY rank (own included) as 8-byte units
+                    // {4 bytes of data, epoch}: vector (row, col) = two 16-byte stores {w0,e,w1,e} {w2,e,w3,e}, one per
+                    // plane.  Consecutive lanes take consecutive units of the peer's block layout (norm_row.cuh), so a
+                    // warp writes 512 contiguous bytes per store instruction.
+                    named_bar_sync(2, 128);   // the four epilogue warps: the tile is staged
+                    const int tid_e = (warp - 2) * 32 + lane, vpr = np >> 3, nvec_t = a.T * vpr;
+                    const bool blocked = (np & 31) == 0;
+                    const int per_blk = a.T * 4;
+                    const int64_t base = a.push_recv_offset + slot_sel * a.push_slot_stride + a.push_rank * a.push_recv_stride;
+                    for (int idx = tid_e; idx < nvec_t; idx += 128) {
+                        int r_, vec;
+                        if (blocked) {
+                            const int blk = idx / per_blk, rem = idx - blk * per_blk;
+                            r_ = rem >> 2;
+                            vec = blk * 4 + (rem & 3);
+                        } else {
+                            r_ = idx / vpr;
+                            vec = idx - r_ * vpr;
+                        }
+                        const int col = p0 + vec * 8;
+                        if (col >= J) continue;
+                        const uint4 o = *reinterpret_cast<const uint4 *>(stg + (static_cast<size_t>(r_) * np + vec * 8) * sizeof(T));
+                        const int64_t off = base + p2p_unit_offset(r_, col, a.T);
+#pragma unroll 1
+                        for (int d = 0; d < a.push_world; ++d) {
+                            const int r = (a.push_rank + d) % a.push_world;
+                            unsigned char *dst = a.push_region[r] + off;
+                            st_relaxed_sys_v4(dst, o.x, epoch, o.y, epoch);
+                            st_relaxed_sys_v4(dst + a.push_plane_bytes, o.z, epoch, o.w, epoch);
+                        }
+                    }
+                    named_bar_sync(2, 128);   // the staging buffer is free for the CTA's next tile
                 }
             } else {
                 // paired tile: accumulator columns [0, np) = first half (rows p0.. of the group), [np, 2 np) =
@@ -681,7 +706,9 @@ bool launch_skinny_gemm(SkinnyArgs a, const void *x, const void *w, int T, int64
     a.w_bytes = kbs * a.n_tile * 128;
     a.x_bytes = kbs * a.t_box * 128;
     a.stage_bytes = a.w_bytes + a.x_bytes;
-    a.stages = std::min(kSkMaxStages, budget / a.stage_bytes);
+    // push epilogue: the finished tile is staged in shared memory behind the ring ([t_box][np] elements)
+    const int stg_bytes = a.epi == kEpiPush ? a.t_box * a.n_tile * 2 : 0;
+    a.stages = std::min(kSkMaxStages, (budget - stg_bytes) / a.stage_bytes);
     if (g_sk_stage_limit > 0) a.stages = std::min(a.stages, g_sk_stage_limit);
     if (a.stages < 2) {
         set_status(kErrUnsupported, "skinny gemm: stage of %d bytes does not fit", a.stage_bytes);
@@ -744,7 +771,7 @@ bool launch_skinny_gemm(SkinnyArgs a, const void *x, const void *w, int T, int64
         if (!make_tiled_map(&mx, x, 3, dims, strides, box, is_bf16)) return false;
     }
     // ring + the rows an M-row A descriptor reads past the last x slab + alignment slack
-    const size_t smem = static_cast<size_t>(a.stages) * a.stage_bytes + a.m * 128 + 1024;
+    const size_t smem = static_cast<size_t>(a.stages) * a.stage_bytes + a.m * 128 + 1024 + stg_bytes;
     const int ctas_per_sm = (half && smem <= 113 * 1024 && a.tmem_cols <= 256) ? 2 : 1;
     const int grid = std::min(a.tiles, di.sm_count * ctas_per_sm);
     cudaError_t e;

@@ -39,6 +39,8 @@ __global__ void __launch_bounds__(512) add_rmsnorm_kernel(const NormArgs a) {
     __shared__ uint32_t s_state[2];
     if (a.trace && threadIdx.x == 0) a.trace[blockIdx.x * 8 + 1] = ops_timer_ns();
     pdl_launch_dependents();
+    uint4 wv[kNormMaxVec];
+    if (a.const_weight) norm_weight_preload(a, wv);   // a model weight: one L2 / HBM round trip off the dependent path
     pdl_wait();
     if (a.trace && threadIdx.x == 0) a.trace[blockIdx.x * 8 + 2] = ops_timer_ns();
     const int row = blockIdx.x;
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(512) add_rmsnorm_kernel(const NormArgs a) {
         e = s_state[0] + 1;               // this all-reduce's epoch
         if (s_state[1] != 0) return;      // a peer failed to arrive earlier: do not wait for it again (block-uniform)
     }
-    const bool failed = add_rmsnorm_row<T, W>(a, row, e, red);
+    const bool failed = add_rmsnorm_row<T, W>(a, row, e, red, a.const_weight ? wv : nullptr);
     if (a.trace && threadIdx.x == 0) a.trace[blockIdx.x * 8 + 3] = ops_timer_ns();
     if (W > 1) {
         if (failed && threadIdx.x == 0) atomicExch(&state[2], 1u);   // error word: a peer never arrived
@@ -89,18 +91,12 @@ __device__ __forceinline__ int32_t total_order_key(float f) {
     int32_t b = __float_as_int(f);
     return b ^ ((b >> 31) & 0x7fffffff);
 }
+// Row argmax by one CTA over `vocab` logits at x; ties -> the LAST index.  Thread 0 returns the result.
 template <typename T>
-__global__ void __launch_bounds__(1024) argmax_kernel(const T *__restrict__ logits, int64_t ld, int vocab,
-                                                      uint32_t *__restrict__ token_out, float *__restrict__ logit_out,
-                                                      float *__restrict__ logits_f32, int64_t ld_f32) {
-    __shared__ int32_t s_key[32];
-    __shared__ int s_idx[32];
-    pdl_launch_dependents();
-    pdl_wait();
-    const int row = blockIdx.x;
-    const T *x = logits + static_cast<int64_t>(row) * ld;
-    int32_t best_key = INT32_MIN;
-    int best_idx = -1;
+__device__ __forceinline__ void row_argmax(const T *__restrict__ x, int vocab, float *__restrict__ logits_f32_row,
+                                           int32_t *s_key, int *s_idx, int32_t &best_key, int &best_idx) {
+    best_key = INT32_MIN;
+    best_idx = -1;
     const int nvec = vocab / 8;
     for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
         float f[8];
@@ -113,8 +109,8 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const T *__restrict__ logi
                 best_idx = v * 8 + j;
             }
         }
-        if (logits_f32) {
-            float4 *o = reinterpret_cast<float4 *>(logits_f32 + static_cast<int64_t>(row) * ld_f32 + v * 8);
+        if (logits_f32_row) {
+            float4 *o = reinterpret_cast<float4 *>(logits_f32_row + v * 8);
             o[0] = make_float4(f[0], f[1], f[2], f[3]);
             o[1] = make_float4(f[4], f[5], f[6], f[7]);
         }
@@ -126,7 +122,7 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const T *__restrict__ logi
             best_key = k;
             best_idx = i;
         }
-        if (logits_f32) logits_f32[static_cast<int64_t>(row) * ld_f32 + i] = f;
+        if (logits_f32_row) logits_f32_row[i] = f;
     }
     auto better = [](int32_t k1, int i1, int32_t k2, int i2) { return k1 > k2 || (k1 == k2 && i1 > i2); };
 #pragma unroll
@@ -150,8 +146,104 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const T *__restrict__ logi
                 best_key = s_key[w];
                 best_idx = s_idx[w];
             }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) argmax_kernel(const T *__restrict__ logits, int64_t ld, int vocab,
+                                                      uint32_t *__restrict__ token_out, float *__restrict__ logit_out,
+                                                      float *__restrict__ logits_f32, int64_t ld_f32) {
+    __shared__ int32_t s_key[32];
+    __shared__ int s_idx[32];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = blockIdx.x;
+    const T *x = logits + static_cast<int64_t>(row) * ld;
+    int32_t best_key;
+    int best_idx;
+    row_argmax<T>(x, vocab, logits_f32 ? logits_f32 + static_cast<int64_t>(row) * ld_f32 : nullptr, s_key, s_idx, best_key, best_idx);
+    if (threadIdx.x == 0) {
         token_out[row] = static_cast<uint32_t>(best_idx < 0 ? 0 : best_idx);
         if (logit_out) logit_out[row] = best_idx < 0 ? 0.f : static_cast<float>(x[best_idx]);
+    }
+}
+
+// Greedy sampling over a vocabulary sharded across tensor-parallel ranks (vocab-parallel lm_head): every rank
+// takes the argmax of its own slice of the logits, stores {key, global index, epoch} into EVERY rank's exchange
+// area over NVLink peer memory as one 16-byte unit (flag and data travel together, as in the all-reduce), polls its
+// own area for the other ranks' candidates and keeps the best under the same order (ties -> the last index): the
+// result is the argmax of the full row, identical on every rank, and `vocab * 2` bytes of lm_head per rank become
+// `vocab * 2 / world`.  Region header words: [16] epoch of the last completed exchange, [17] CTA arrival counter.
+struct ArgmaxTpArgs {
+    const void *logits;        // [T, rows] this rank's slice
+    int64_t ld;
+    int rows, row0;            // slice size and its first global index
+    uint32_t *token_out;
+    float *logit_out;
+    unsigned char *region[8];  // every rank's region (own: local pointer)
+    int64_t exch_offset;       // byte offset of the exchange area: [2 parities][8 ranks][128 rows] x 16 bytes
+    int rank, world;
+    unsigned long long timeout_ns;
+};
+constexpr int kArgmaxMaxRows = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(1024) argmax_tp_kernel(const ArgmaxTpArgs a) {
+    __shared__ int32_t s_key[32];
+    __shared__ int s_idx[32];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = blockIdx.x;
+    const T *x = static_cast<const T *>(a.logits) + static_cast<int64_t>(row) * a.ld;
+    int32_t best_key;
+    int best_idx;
+    row_argmax<T>(x, a.rows, nullptr, s_key, s_idx, best_key, best_idx);
+    if (threadIdx.x != 0) return;
+    uint32_t *state = reinterpret_cast<uint32_t *>(a.region[a.rank]);
+    const uint32_t e = *reinterpret_cast<volatile uint32_t *>(&state[16]) + 1;
+    if (*reinterpret_cast<volatile uint32_t *>(&state[2]) != 0) return;   // a peer failed earlier
+    const int64_t base = a.exch_offset + static_cast<int64_t>(e & 1u) * 8 * kArgmaxMaxRows * 16;
+    const uint32_t gidx = static_cast<uint32_t>(a.row0 + (best_idx < 0 ? 0 : best_idx));
+    for (int d = 0; d < a.world; ++d) {
+        const int r = (a.rank + d) % a.world;
+        unsigned char *dst = a.region[r] + base + (static_cast<int64_t>(a.rank) * kArgmaxMaxRows + row) * 16;
+        asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(static_cast<uint32_t>(best_key)),
+                     "r"(gidx), "r"(e), "r"(0u)
+                     : "memory");
+    }
+    int32_t k_best = INT32_MIN;
+    uint32_t i_best = 0;
+    bool failed = false;
+    const unsigned long long t0 = ops_timer_ns();
+    for (int r = 0; r < a.world && !failed; ++r) {
+        const unsigned char *src = a.region[a.rank] + base + (static_cast<int64_t>(r) * kArgmaxMaxRows + row) * 16;
+        uint4 v;
+        for (int spin = 0;; ++spin) {
+            v = ld_volatile_v4(src);
+            if (v.z == e) break;
+            if ((spin & 63) == 63 && ops_timer_ns() - t0 > a.timeout_ns) {
+                failed = true;
+                break;
+            }
+        }
+        if (failed) break;
+        const int32_t k = static_cast<int32_t>(v.x);
+        if (r == 0 || k > k_best || (k == k_best && v.y > i_best)) {   // ties -> the last (largest) global index
+            k_best = k;
+            i_best = v.y;
+        }
+    }
+    if (failed) {
+        atomicExch(&state[2], 1u);
+    } else {
+        a.token_out[row] = i_best;
+        if (a.logit_out) a.logit_out[row] = __int_as_float(k_best ^ ((k_best >> 31) & 0x7fffffff));   // the key map is an involution
+    }
+    __threadfence();
+    if (atomicAdd(&state[17], 1u) == gridDim.x - 1) {
+        state[17] = 0;
+        __threadfence();
+        state[16] = e;
     }
 }
 
@@ -171,6 +263,7 @@ void prefer_max_carveout_once() {
     set(add_rmsnorm_kernel<__half, 4>); set(add_rmsnorm_kernel<__half, 8>);
     set(embedding_kernel<__nv_bfloat16>); set(embedding_kernel<__half>);
     set(argmax_kernel<__nv_bfloat16>); set(argmax_kernel<__half>);
+    set(argmax_tp_kernel<__nv_bfloat16>); set(argmax_tp_kernel<__half>);
     cudaGetLastError();
     attr_dev = di.ordinal;
 }
@@ -232,6 +325,7 @@ bool launch_add_rmsnorm(const void *x, const void *residual, void *residual_out,
     // reduction order as the fused tail of the row-parallel projections (gemm_skinny.cu), hence the same bits
     int threads = std::min(nvec > 256 * kNormMaxVec ? 512 : 256, (nvec + 31) / 32 * 32);
     prefer_max_carveout_once();
+    a.const_weight = (launch_flags() & kLaunchConstWeights) ? 1 : 0;
     a.trace = a.T <= kStepTraceCtas ? next_step_trace_slot(a.world > 1 ? "add_rmsnorm recv" : "add_rmsnorm") : nullptr;
     cudaError_t e = dtype == 1 ? launch_norm<__nv_bfloat16>(a, threads, stream) : launch_norm<__half>(a, threads, stream);
     note_launch();
@@ -288,6 +382,37 @@ bool launch_argmax(const void *logits, int64_t T, int64_t vocab, int64_t ld, uin
         return false;
     }
     return check_launch("argmax_kernel");
+}
+
+bool launch_argmax_tp(const void *logits, int64_t T, int64_t rows, int64_t row0, int64_t ld, uint32_t dtype,
+                      uint32_t *token_out, float *logit_out, void *const *regions, int rank, int world, int64_t slot_bytes,
+                      cudaStream_t stream) {
+    if (T <= 0) return true;
+    // the exchange area is the first staging slot of the region (unused by the fused push / receive all-reduce)
+    if (dtype > 1 || rows <= 0 || !logits || !token_out || !al16(logits) || ld % 8 || T > kArgmaxMaxRows || !regions ||
+        world < 2 || world > 8 || rank < 0 || rank >= world || slot_bytes < 2 * 8 * kArgmaxMaxRows * 16) {
+        set_status(kErrInvalidArg,
+                   "atoma_sample_greedy_tp: 16-bit logits with 16-byte aligned rows, T <= %d, world 2..8, slot_bytes >= %d",
+                   kArgmaxMaxRows, 2 * 8 * kArgmaxMaxRows * 16);
+        return false;
+    }
+    prefer_max_carveout_once();
+    ArgmaxTpArgs a{};
+    a.logits = logits; a.ld = ld;
+    a.rows = static_cast<int>(rows); a.row0 = static_cast<int>(row0);
+    a.token_out = token_out; a.logit_out = logit_out;
+    for (int r = 0; r < 8; ++r) a.region[r] = static_cast<unsigned char *>(regions[r < world ? r : rank]);
+    a.exch_offset = 4096;   // kArHeaderBytes: staging slot 0
+    a.rank = rank; a.world = world;
+    a.timeout_ns = 30000000000ull;
+    cudaError_t e = dtype == 1 ? launch_ex(argmax_tp_kernel<__nv_bfloat16>, dim3(static_cast<unsigned>(T)), dim3(1024), 0, stream, a)
+                               : launch_ex(argmax_tp_kernel<__half>, dim3(static_cast<unsigned>(T)), dim3(1024), 0, stream, a);
+    note_launch();
+    if (e != cudaSuccess) {
+        set_status(static_cast<int>(e), "argmax_tp_kernel: %s", cudaGetErrorString(e));
+        return false;
+    }
+    return check_launch("argmax_tp_kernel");
 }
 
 }  // namespace atoma

@@ -29,6 +29,9 @@ bool launch_embedding(const uint32_t *tokens, const void *table, void *out, int6
                       int64_t ld_table, int64_t ldo, uint32_t dtype, cudaStream_t stream);
 bool launch_argmax(const void *logits, int64_t T, int64_t vocab, int64_t ld, uint32_t dtype, uint32_t *token_out,
                    float *logit_out, float *logits_f32, int64_t ld_f32, cudaStream_t stream);
+bool launch_argmax_tp(const void *logits, int64_t T, int64_t rows, int64_t row0, int64_t ld, uint32_t dtype,
+                      uint32_t *token_out, float *logit_out, void *const *regions, int rank, int world, int64_t slot_bytes,
+                      cudaStream_t stream);
 void p2p_layout(int64_t slot_bytes, int64_t *recv_offset, int64_t *slot_stride, int64_t *recv_stride);
 int try_launch_decode_paged(const MhaParams &p, bool is_bf16, int64_t max_units_hint, cudaStream_t stream);
 void set_next_decode_stable_cache(int v);
@@ -176,10 +179,10 @@ bool gemm_tn_push(const void *x, const void *w, int64_t T, int64_t N, int64_t K,
                   void *const *regions, int rank, int world, int64_t slot_bytes, uint32_t dtype, cudaStream_t stream,
                   const NormArgs *tail = nullptr) {
     if (T <= 0 || N <= 0) return true;
-    if (dtype > 1 || !regions || world < 2 || world > 8 || (world & (world - 1)) || rank < 0 || rank >= world || N % 8 ||
+    if (dtype > 1 || !regions || world < 2 || world > 8 || (world & (world - 1)) || rank < 0 || rank >= world || N % 32 ||
         T * N * 2 > slot_bytes || !x || !w || !al16(x) || !al16(w) || ldx % 8 || ldw % 8 || ldx < K || ldw < K) {
         set_status(kErrInvalidArg,
-                   "atoma_gemm_tn_push: world 2/4/8, 0 <= rank < world, N a multiple of 8, T*N*2 <= slot_bytes, aligned "
+                   "atoma_gemm_tn_push: world 2/4/8, 0 <= rank < world, N a multiple of 32, T*N*2 <= slot_bytes, aligned "
                    "operands (T=%lld N=%lld rank=%d world=%d slot=%lld)",
                    static_cast<long long>(T), static_cast<long long>(N), rank, world, static_cast<long long>(slot_bytes));
         return false;
@@ -299,6 +302,14 @@ extern "C" void atoma_sample_greedy(const void *logits, int64_t T, int64_t vocab
                                     atoma_stream_t stream) {
     clear_status();
     launch_argmax(logits, T, vocab, ld, dtype, token_out, logit_out, logits_f32, ld_f32, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" void atoma_sample_greedy_tp(const void *logits, int64_t T, int64_t rows, int64_t row0, int64_t ld, uint32_t dtype,
+                                       uint32_t *token_out, float *logit_out, void *const *regions, int rank, int world,
+                                       int64_t slot_bytes, atoma_stream_t stream) {
+    clear_status();
+    launch_argmax_tp(logits, T, rows, row0, ld, dtype, token_out, logit_out, regions, rank, world, slot_bytes,
+                     static_cast<cudaStream_t>(stream));
 }
 
 extern "C" void atoma_gemm_tn_push(const void *x, const void *w, int64_t T, int64_t N, int64_t K, int64_t ldx,
@@ -488,6 +499,20 @@ extern "C" void atoma_llama_decode_step(const atoma_llama_model *model, const at
                             m.rms_eps, dt, world > 1 ? m.p2p_regions[m.tp_rank] : nullptr, m.p2p_slot_bytes, world, stream))
         return;
     if (!m.lm_head) return;
+    if (world > 1 && m.lm_head_rows > 0) {
+        // vocab-parallel head: this rank's slice of the logits, then the candidates are exchanged over peer memory
+        if (b.logits || b.logits_f32 || !b.next_tokens || m.lm_head_rows % 8 || m.lm_head_row0 < 0 ||
+            m.lm_head_row0 + m.lm_head_rows > m.vocab) {
+            set_status(kErrInvalidArg, "atoma_llama_decode_step: a vocab-parallel head (lm_head_rows = %lld, a multiple of 8 inside "
+                                       "the vocabulary) returns next_tokens / next_logits only",
+                       static_cast<long long>(m.lm_head_rows));
+            return;
+        }
+        if (!gemm_tn(final_normed, m.lm_head, s.logits, T, m.lm_head_rows, hid, hid, hid, m.lm_head_rows, dt, stream)) return;
+        launch_argmax_tp(s.logits, T, m.lm_head_rows, m.lm_head_row0, m.lm_head_rows, dt, b.next_tokens, b.next_logits,
+                         m.p2p_regions, m.tp_rank, world, m.p2p_slot_bytes, stream);
+        return;
+    }
     // logits = lm_head(x)  (llama.rs:476; every token of a decode batch is selected), greedy sample
     void *logits = b.logits ? b.logits : s.logits;
     if (!gemm_tn(final_normed, m.lm_head, logits, T, m.vocab, hid, hid, hid, m.vocab, dt, stream)) return;

@@ -29,7 +29,16 @@ struct NormArgs {
     int world;
     unsigned long long timeout_ns;
     unsigned long long *trace;   // diagnostics (step timeline): [cta][8] = {-, start, dependency resolved, end}
+    int const_weight;            // the norm weight is immutable (model weight): load it before the grid dependency resolves
 };
+
+// Receive-buffer layout of the fused all-reduce (one plane of a source rank's [T, N] addend; the second plane lies
+// plane_bytes further): 32-column blocks, inside a block row-major 64-byte rows — so that the [T, 32k] tile a GEMM
+// CTA owns is ONE contiguous run of the peer's memory and a warp's 32 x 16-byte stores coalesce into full NVLink
+// packets (row-major [T, N] made every 16-byte store its own packet: 34 us per 8-rank all-reduce, measured).
+__device__ __forceinline__ int64_t p2p_unit_offset(int row, int col, int T) {
+    return ((static_cast<int64_t>(col >> 5) * T + row) * 4 + ((col & 31) >> 3)) * 16;
+}
 
 namespace normrow {
 
@@ -85,11 +94,24 @@ __device__ __forceinline__ float block_sum(float v, float *red) {
 
 }  // namespace normrow
 
+// This thread's vectors of the norm weight (call before griddepcontrol.wait when the weight is immutable).
+__device__ __forceinline__ void norm_weight_preload(const NormArgs &a, uint4 (&wv)[kNormMaxVec]) {
+    const int nvec = a.hidden / 8;
+#pragma unroll
+    for (int u = 0; u < kNormMaxVec; ++u) {
+        const int v = threadIdx.x + u * blockDim.x;
+        wv[u] = (v < nvec && a.weight) ? *reinterpret_cast<const uint4 *>(static_cast<const unsigned char *>(a.weight) + v * 16)
+                                       : make_uint4(0, 0, 0, 0);
+    }
+}
+
 // One row by the whole CTA (every thread must call it; thread t owns the 16-byte vectors t, t + blockDim, ...).
 // `e` = the all-reduce's epoch (W > 1).  `red`: >= 32 floats of shared memory, reusable after the call returns and
 // a __syncthreads().  Returns true if a peer failed to arrive in time (W > 1; CTA-uniform) — nothing was normalised.
+// `wpre`: the thread's weight vectors from norm_weight_preload(), or null (loaded here).
 template <typename T, int W>
-__device__ __forceinline__ bool add_rmsnorm_row(const NormArgs &a, int row, uint32_t e, float *red) {
+__device__ __forceinline__ bool add_rmsnorm_row(const NormArgs &a, int row, uint32_t e, float *red,
+                                                const uint4 *wpre = nullptr) {
     using namespace normrow;
     const int nvec = a.hidden / 8;
     bool failed = false;
@@ -102,8 +124,7 @@ __device__ __forceinline__ bool add_rmsnorm_row(const NormArgs &a, int row, uint
         float x[8];
         if (W > 1) {
             // poll the W addends of vector i (8-byte units {data, epoch}); add in rank order, round once
-            const int64_t i = static_cast<int64_t>(row) * nvec + v;
-            const unsigned char *src = a.region + a.recv_offset + (e & 1u) * a.slot_stride + i * 16;
+            const unsigned char *src = a.region + a.recv_offset + (e & 1u) * a.slot_stride + p2p_unit_offset(row, v * 8, a.T);
             uint4 lo[W > 1 ? W : 1], hi[W > 1 ? W : 1];
             bool done[W > 1 ? W : 1];
 #pragma unroll
@@ -169,7 +190,7 @@ __device__ __forceinline__ bool add_rmsnorm_row(const NormArgs &a, int row, uint
             const int v = threadIdx.x + u * blockDim.x;
             if (v >= nvec) break;
             float w[8], o[8];
-            unpack8f<T>(*reinterpret_cast<const uint4 *>(static_cast<const T *>(a.weight) + v * 8), w);
+            unpack8f<T>(wpre ? wpre[u] : *reinterpret_cast<const uint4 *>(static_cast<const T *>(a.weight) + v * 8), w);
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = scale * h[u][j] * w[j];
             *reinterpret_cast<uint4 *>(static_cast<T *>(a.normed) + static_cast<int64_t>(row) * a.ldn + v * 8) = pack8f<T>(o);

@@ -185,7 +185,7 @@ class DecodeStep:
 
     def __init__(self, shard: LlamaShard, kv_caches: List[torch.Tensor], max_batch: int, p2p=None,
                  want_logits: bool = False, want_logits_f32: bool = False, want_hidden: bool = False,
-                 no_comm: bool = False):
+                 no_comm: bool = False, vocab_parallel_head: Optional[bool] = None):
         cfg = shard.cfg
         if max_batch < 1 or max_batch > 128:
             raise AtomaError("the decode-step executor takes 1..128 sequences per step")
@@ -224,6 +224,19 @@ class DecodeStep:
         if p2p is not None:
             m.p2p_regions = C.cast(p2p._regions, C.POINTER(C.c_void_p))
             m.p2p_slot_bytes = p2p.slot_bytes
+        # Vocab-parallel head (tensor parallel, sampled tokens only): this rank multiplies by its [vocab / world, hidden]
+        # slice of lm_head and the ranks exchange their argmax candidates (atoma_sample_greedy_tp).  The reference
+        # replicates lm_head on every rank (llama_nccl.rs:320-321); the sampled tokens are identical.
+        can_vp = (p2p is not None and shard.lm_head is not None and not want_logits and not want_logits_f32 and
+                  cfg.vocab_size % (8 * shard.world) == 0 and p2p.slot_bytes >= 32768)
+        if vocab_parallel_head and not can_vp:
+            raise AtomaError("a vocab-parallel head needs tensor parallelism, vocab % (8 * world) == 0, p2p slots of >= 32 KiB "
+                             "and returns sampled tokens only (no logits)")
+        self.vocab_parallel_head = can_vp if vocab_parallel_head is None else bool(vocab_parallel_head)
+        if self.vocab_parallel_head:
+            rows = cfg.vocab_size // shard.world
+            m.lm_head_rows, m.lm_head_row0 = rows, rows * shard.rank
+            m.lm_head = shard.lm_head.data_ptr() + rows * shard.rank * shard.lm_head.stride(0) * shard.lm_head.element_size()
         self._model = m
         self.max_batch = max_batch
         L = _lib.lib()

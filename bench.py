@@ -418,6 +418,12 @@ def tp_parity(torch, args, cfg, batch, ctx, layers, rank, world, dev, arm, dist)
         dist.barrier()
         got = (st.logits if head else st.hidden_out)[:batch].float()
         tok = st.next_tokens[:batch].clone() if head else None
+        if head and getattr(arm.step, "vocab_parallel_head", False):
+            # the timed step samples through the vocab-parallel head; `st` has the replicated head: same tokens, same logits
+            arm.step.run()
+            torch.cuda.synchronize()
+            res["vocab_parallel_tokens_identical"] = bool(torch.equal(arm.step.next_tokens[:batch], tok) and
+                                                          torch.equal(arm.step.next_logits[:batch], st.next_logits[:batch]))
         if rank == 0:
             w1 = Workload(torch, cfg, batch, ctx, 0, 1, nl, dev)
             s1 = DecodeStep(w1.shard.prefix(nl, with_head=head), w1.kv, max_batch=batch, want_logits=head, want_hidden=not head)
@@ -438,7 +444,8 @@ def tp_parity(torch, args, cfg, batch, ctx, layers, rank, world, dev, arm, dist)
             torch.cuda.empty_cache()
         dist.barrier()
     if rank == 0:
-        res["ok"] = bool(res["one_layer_max_ulp"] <= 8.0 and res["one_layer_rel_err"] <= 6e-3 and res["logits_rel_err"] <= 5e-2)
+        res["ok"] = bool(res["one_layer_max_ulp"] <= 8.0 and res["one_layer_rel_err"] <= 6e-3 and res["logits_rel_err"] <= 5e-2 and
+                         res.get("vocab_parallel_tokens_identical", True))
         res["how"] = ("rank 0 rebuilds the tp=1 model and caches from the same seeds and reruns the step; one_layer = 1 layer, "
                       "no head (2 all-reduces), full_step = the timed configuration")
     return res
@@ -660,6 +667,10 @@ def main():
         ms_step = ms_dev / args.steps
         ms_step_e2e = ms_e2e / args.steps
         step_bytes = wl.shard.weight_bytes() + layers * wl.kv_bytes_per_layer()   # per rank: all weights + all KV once
+        vocab_parallel = args.impl == "ours" and getattr(arm.step, "vocab_parallel_head", False)
+        if vocab_parallel:   # this rank streams only its [vocab / tp, hidden] slice of lm_head
+            lm = wl.shard.lm_head
+            step_bytes -= lm.numel() * lm.element_size() * (tp - 1) // tp
         if wl.shard.embed is not None and wl.shard.embed is not wl.shard.lm_head:
             pass   # the embedding table is gathered (batch rows), not streamed
         line = {
@@ -692,7 +703,10 @@ def main():
                 "gemm": ("atoma tcgen05 kernels (gemm_skinny.cu: fused qkv+RoPE+cache write, o_proj, fused gate_up+SwiGLU, "
                          "down_proj, lm_head)" if args.impl == "ours" else
                          "cuBLAS via torch.matmul (as in the reference: candle Linear -> cuBLAS), q/k/v and gate/up as separate calls"),
-                "sampling": "greedy on the device (argmax kernel), 8 bytes per sequence to the host" if args.impl == "ours" else
+                "sampling": ("greedy on the device (argmax kernel), 8 bytes per sequence to the host" +
+                             ("; vocab-parallel head: each rank multiplies by its 1/tp slice of lm_head and the ranks exchange their "
+                              "argmax candidates over NVLink peer memory (same tokens as the replicated head: tp_parity."
+                              "vocab_parallel_tokens_identical)" if vocab_parallel else "")) if args.impl == "ours" else
                             "logits row to the host per sequence + host argmax (model_executor.rs:227-262)",
                 "wall_ms_per_step": t_wall * 1e3 / args.steps,
                 "hbm_bytes_per_step_per_rank": step_bytes,

@@ -99,11 +99,24 @@ void atoma_sample_greedy(const void *logits, int64_t T, int64_t vocab, int64_t l
                          atoma_stream_t stream);
 
 /*
+ * Greedy sampling over a vocabulary sharded across tensor-parallel ranks: logits [T, rows] is this rank's slice
+ * (global indices row0 .. row0 + rows); every rank stores its row candidates {order key, global index, epoch} into
+ * every rank's region (first staging slot; one 16-byte unit per candidate) and keeps the best of all ranks' — the
+ * argmax of the full row with atoma_sample_greedy's tie rule, identical on every rank.  Must be called by every
+ * rank in the same order; T <= 128; slot_bytes >= 32 KiB.
+ */
+void atoma_sample_greedy_tp(const void *logits, int64_t T, int64_t rows, int64_t row0, int64_t ld, uint32_t dtype,
+                            uint32_t *token_out, float *logit_out, void *const *regions, int rank, int world,
+                            int64_t slot_bytes, atoma_stream_t stream);
+
+/*
  * Tensor-parallel row-parallel projection with the all-reduce fused in (row f4; multi_gpu.rs:141-179).
  * Send side: atoma_gemm_tn_push computes this rank's partial y[T,N] = x[T,K_shard] w^T and its
  * epilogue stores the bf16/f16 partial tile straight into every rank's receive buffer over NVLink
- * (regions[r]: the peer-mapped regions of atoma_p2p_alloc/export/import, slot_bytes >= T*N*2; 8-byte
- * units {4 bytes of data, epoch}) — no staging buffer, no separate all-reduce launch.
+ * (regions[r]: the peer-mapped regions of atoma_p2p_alloc/export/import, slot_bytes >= T*N*2, N % 32 == 0;
+ * 8-byte units {4 bytes of data, epoch}, laid out in 32-column blocks so that a CTA's tile is one contiguous
+ * run of the peer's memory and a warp's stores coalesce) — no staging buffer in global memory, no separate
+ * all-reduce launch.
  * Receive side: atoma_allreduce_recv_add_rmsnorm polls the local receive buffers, adds the `world`
  * addends in fp32 in rank order and rounds once (bit-identical on every rank), then continues exactly
  * like atoma_add_rmsnorm with that sum as x.  The pair must be called by every rank in the same order;
@@ -148,6 +161,11 @@ typedef struct atoma_llama_model {
     int32_t tp_rank, tp_world;
     void *const *p2p_regions;
     int64_t p2p_slot_bytes;
+    /* vocab-parallel head (tp_world > 1 only; 0 rows = lm_head is the full [vocab, hidden] matrix, replicated as in
+     * llama_nccl.rs:320-321): lm_head points at rows [lm_head_row0, lm_head_row0 + lm_head_rows) of the matrix, a
+     * multiple of 8 rows; the step then returns next_tokens / next_logits only (each rank takes the argmax of its
+     * slice and the ranks exchange their candidates over peer memory — atoma_sample_greedy_tp). */
+    int64_t lm_head_rows, lm_head_row0;
 } atoma_llama_model;
 
 typedef struct atoma_decode_batch {

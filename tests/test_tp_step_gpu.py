@@ -115,7 +115,7 @@ def _worker(rank, world, port, out_dir):
     ops.set_launch_mode()
 
     # ---- (2) the whole tensor-parallel step vs tp = 1 ----
-    cfg = LlamaConfig(hidden_size=hidden, intermediate_size=2048, vocab_size=4000, num_hidden_layers=3,
+    cfg = LlamaConfig(hidden_size=hidden, intermediate_size=2048, vocab_size=4096, num_hidden_layers=3,
                       num_attention_heads=16, num_key_value_heads=8, max_position_embeddings=128)
     res = {}
     for tag, nl, head in (("one_layer", 1, False), ("full", 3, True)):
@@ -125,6 +125,30 @@ def _worker(rank, world, port, out_dir):
         st.launch()
         torch.cuda.synchronize()
         got = (st.logits if head else st.hidden_out)[:T].float()
+        if head:
+            # vocab-parallel head: every rank multiplies by its slice of lm_head and the ranks exchange their argmax
+            # candidates over peer memory — same sampled tokens and logits as the replicated head, on every rank,
+            # eagerly twice (epoch parity) and replayed from a graph
+            assert not st.vocab_parallel_head
+            vp = DecodeStep(shard.prefix(nl, with_head=True), kv, max_batch=T, p2p=comm)
+            assert vp.vocab_parallel_head
+            vp.bind(tokens, pos, slots, bt, lens)
+            for rep in range(2):
+                vp.next_tokens.zero_(); vp.next_logits.zero_()
+                vp.launch()
+                torch.cuda.synchronize()
+                if not (torch.equal(vp.next_tokens[:T], st.next_tokens[:T]) and torch.equal(vp.next_logits[:T], st.next_logits[:T])):
+                    bad.append((tag, "vocab-parallel sampling differs (eager)", rep))
+            dist.barrier()
+            vp.capture()
+            for rep in range(3):
+                vp.next_tokens.zero_(); vp.next_logits.zero_()
+                vp.run()
+                torch.cuda.synchronize()
+                if not (torch.equal(vp.next_tokens[:T], st.next_tokens[:T]) and torch.equal(vp.next_logits[:T], st.next_logits[:T])):
+                    bad.append((tag, "vocab-parallel sampling differs (graph)", rep))
+            dist.barrier()
+            vp.release()
         outs = [torch.empty_like(got.cpu()) for _ in range(world)]
         dist.all_gather(outs, got.cpu())
         for r in range(1, world):
