@@ -436,6 +436,11 @@ def tp_parity(torch, args, cfg, batch, ctx, layers, rank, world, dev, arm, dist)
             if head:
                 res["logits_rel_err"] = rel
                 res["greedy_agreement"] = (tok == s1.next_tokens[:batch]).float().mean().item()
+                # Where the greedy tokens differ the choice was a near-tie (a random-init model has a flat head): how far
+                # below the tp=1 maximum the tp=1 logit of the token the TP step chose lies, in units of the row's logit
+                # standard deviation (worst sequence).
+                chosen = want.gather(1, tok.long().unsqueeze(1)).squeeze(1)
+                res["greedy_choice_gap_sigma_max"] = ((want.max(dim=-1).values - chosen) / want.std(dim=-1)).max().item()
             else:
                 ulp = torch.exp2(torch.floor(torch.log2(want.pow(2).mean(dim=-1, keepdim=True).sqrt().clamp_min(2.0 ** -126))) - 7)   # bf16 ulp at the row's rms
                 res["one_layer_max_ulp"] = (diff / ulp).max().item()

@@ -84,6 +84,23 @@ def main():
         res[f"reshape_T{T}"] = r
         print("reshape_and_cache_flash", json.dumps(r), flush=True)
 
+    # ---- the host link's own peak: ONE contiguous 512 MiB cudaMemcpyAsync each way, pinned memory (the denominator
+    # of the swap numbers below; PCIe Gen5 x16 nominal 63 GB/s per direction) ----
+    big_d = torch.empty(512 << 20, dtype=torch.uint8, device=DEV)
+    big_h = torch.empty(512 << 20, dtype=torch.uint8).pin_memory()
+    link = {}
+    for name, (dst, src) in (("h2d", (big_d, big_h)), ("d2h", (big_h, big_d))):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        link[name + "_GBps"] = 3 * big_d.numel() / (time.perf_counter() - t0) / 1e9
+    res["host_link_peak"] = link
+    print("host_link_peak", json.dumps(link), flush=True)
+    del big_d, big_h
+
     # ---- swap_blocks: whole sequences (256 blocks) of one layer's K, GPU <-> pinned host ----
     for nseq in (1, 8, 64):
         nblk = nseq * 256
@@ -107,7 +124,8 @@ def main():
                 fn()
             torch.cuda.synchronize()
             t = (time.perf_counter() - t0) / 3
-            r = {"blocks": nblk, "bytes": byts, "ours_ms": t * 1e3, "ours_GBps": byts / t / 1e9}
+            r = {"blocks": nblk, "bytes": byts, "ours_ms": t * 1e3, "ours_GBps": byts / t / 1e9,
+                 "frac_of_host_link_peak": byts / t / 1e9 / link["d2h_GBps" if name == "out" else "h2d_GBps"]}
             # the reference: one memcpy per block, issued from the host (cache_manager.rs:18-128, ops.rs:158-216)
             pairs = list((out_map if name == "out" else in_map).items())
             s_t, d_t = (c, host) if name == "out" else (host, c)
