@@ -212,7 +212,12 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
                 mbar_wait(&empty[stage], phase ^ 1);   // passes at once during the first trip round the ring
                 unsigned char *dst = ring + stage * a.stage_bytes;
                 if (is_w && a.trigger_late && n == max(total - a.trigger_late, 0)) pdl_launch_dependents();
-                if (a.trace && is_w && lane == 0 && (n == 0 || n == total - 1)) a.trace[blockIdx.x * 8 + (n == 0 ? 4 : 5)] = sk_timer_ns();
+                if (a.trace && is_w && lane == 0 && n == total - 1) a.trace[blockIdx.x * 8 + 5] = sk_timer_ns();
+                if (a.trace && is_w && lane == 0 && n == 0) {
+                    unsigned smid;
+                    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                    a.trace[blockIdx.x * 8 + 4] = smid;   // which SM ran this CTA (hand-over analysis: scripts/trace_step.py)
+                }
                 if (elect_one_sync()) {
                     // W is read exactly once by exactly one CTA: evict-first.  x is re-read by every CTA: keep it.
                     if (is_w) {

@@ -66,6 +66,7 @@ def main():
     # traced kernels of the captured step: the second half of the labels
     idx = [i for i in range(len(labels))][len(labels) // 2:]
     t0 = None
+    last_end_on_sm, last_kernel_name = {}, None
     prev_end = None
     prev_last_land = None
     for i in idx:
@@ -76,7 +77,7 @@ def main():
             start, end = k[live, 0], k[live, 3]
             first_land, last_land = k[live, 1], k[live, 7]
             dep = k[live, 6]
-            first_issue = k[live, 4]
+            first_issue = k[live, 0]
         elif name.startswith("decode"):
             live = k[:, 3] > 0
             start, end = k[live, 1], k[live, 3]
@@ -105,6 +106,20 @@ def main():
         if prev_end is not None:
             rec["start_minus_prev_end"] = round(rec["first_cta_start"] - prev_end, 2)
         prev_end = rec["end"]
+        # SM hand-over: for every SM, this kernel's CTA start minus the end of the previous traced CTA on that SM
+        sm = (k[live, 4] if name.startswith("gemm") else k[live, 0] if name.startswith("decode") else None)
+        if sm is not None:
+            d = []
+            for s_, st_, en_ in zip(sm.tolist(), start.tolist(), end.tolist()):
+                if s_ in last_end_on_sm:
+                    d.append((st_ - last_end_on_sm[s_][0]) / 1e3)
+            if d:
+                d = np.asarray(d)
+                rec["handover_us"] = {"after": last_kernel_name, "n": int(d.size), "min": round(float(d.min()), 2),
+                                      "median": round(float(np.median(d)), 2), "max": round(float(d.max()), 2)}
+            for s_, en_ in zip(sm.tolist(), end.tolist()):
+                last_end_on_sm[s_] = (en_, name)
+            last_kernel_name = name
         rows.append(rec)
     (ROOT / args.out).parent.mkdir(exist_ok=True)
     (ROOT / args.out).write_text(json.dumps(rows, indent=1))
