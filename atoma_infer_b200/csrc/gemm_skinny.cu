@@ -122,6 +122,193 @@ __device__ __forceinline__ void store8(T *dst, const uint4 &v, int valid, bool v
     }
 }
 
+// Per-row state of an epilogue thread (thread = token row).
+template <typename T>
+struct EpiRow {
+    int row;
+    bool row_ok;
+    T *y;                 // this row of the output
+    bool y_vec;
+    const T *cos_r, *sin_r;
+    int64_t cache_row;
+    uint32_t epoch;
+    int slot_sel;
+    unsigned char *stg;   // push epilogue: shared-memory staging of the tile
+};
+
+template <typename T, int M, int EPI>
+__device__ __forceinline__ EpiRow<T> epi_row_init(const SkinnyArgs &a, int warp, int lane, unsigned char *stg) {
+    EpiRow<T> r;
+    const int quad = warp & 3;   // the TMEM lane quadrant this warp may read
+    // M = 64: accumulator row r lives in lane (r % 16) + 32 (r / 16); M = 128: row r in lane r.
+    r.row = (M == 64) ? quad * 16 + lane : quad * 32 + lane;
+    r.row_ok = (M == 64 ? lane < 16 : true) && r.row < a.T;
+    r.y = static_cast<T *>(a.y) + static_cast<int64_t>(r.row_ok ? r.row : 0) * a.ldy;
+    r.y_vec = (a.ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0);
+    r.cos_r = r.sin_r = nullptr;
+    r.cache_row = -1;
+    if (EPI == kEpiRope && r.row_ok) {
+        const int64_t pos = a.positions[r.row];
+        r.cos_r = static_cast<const T *>(a.cos) + pos * a.rot_stride;
+        r.sin_r = static_cast<const T *>(a.sin) + pos * a.rot_stride;
+        const int64_t slot = a.slot_mapping ? a.slot_mapping[r.row] : -1;   // < 0: padded token (cache_manager.cu:151-155)
+        if (slot >= 0 && a.k_cache)
+            r.cache_row = (slot / a.block_size) * a.block_stride + (slot % a.block_size) * a.num_kv_heads * (2 * a.J);
+    }
+    r.epoch = 0;
+    r.slot_sel = 0;
+    r.stg = stg;
+    if (EPI == kEpiPush) {
+        r.epoch = a.push_state[0] + 1;   // this all-reduce's epoch (advanced by the receive-side kernel)
+        r.slot_sel = static_cast<int>(r.epoch & 1u);
+    }
+    return r;
+}
+
+// The epilogue of ONE finished tile (group g, first row p0 of the group) whose accumulator starts at TMEM address
+// `tacc` (lane quadrant included), by the four epilogue warps.
+template <typename T, int M, int EPI>
+__device__ __forceinline__ void epilogue_tile(const SkinnyArgs &a, const EpiRow<T> &er, uint32_t tacc, int g, int p0, int warp,
+                                              int lane) {
+    const int J = a.J, np = a.np;
+    const int row = er.row;
+    const bool row_ok = er.row_ok;
+    T *y = er.y;
+    const bool y_vec = er.y_vec;
+    const T *cos_r = er.cos_r, *sin_r = er.sin_r;
+    const int64_t cache_row = er.cache_row;
+    const uint32_t epoch = er.epoch;
+    const int slot_sel = er.slot_sel;
+    unsigned char *stg = er.stg;
+    // 8 consecutive columns of the tile: the sum of the nacc partial accumulators (fixed order)
+    auto load8 = [&](int col, uint32_t (&v)[8]) {
+        tmem_ld_32x32b_x8(tacc + col, v);
+        for (int i = 1; i < a.nacc; ++i) {
+            uint32_t w[8];
+            tmem_ld_32x32b_x8(tacc + i * a.acc_stride + col, w);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+        }
+    };
+
+    if (EPI == kEpiPlain || EPI == kEpiPush) {
+        // columns [p0, p0 + np) of the output, 8 at a time, two TMEM loads in flight
+        for (int c = 0; c < np; c += 16) {
+            uint32_t v0[8], v1[8];
+            load8(c, v0);
+            if (c + 8 < np) load8(c + 8, v1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int j0 = p0 + c + 8 * u;
+                if (c + 8 * u >= np || j0 >= J || !row_ok) continue;
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(u == 0 ? v0[i] : v1[i]);
+                const uint4 o = pack8<T>(f);
+                if (EPI == kEpiPlain) {
+                    store8<T>(y + j0, o, J - j0, y_vec);
+                } else {
+                    // tensor parallel: stage the tile in shared memory; pushed below, coalesced
+                    *reinterpret_cast<uint4 *>(stg + (static_cast<size_t>(row) * np + c + 8 * u) * sizeof(T)) = o;
+                }
+            }
+        }
+        if (EPI == kEpiPush) {
+            // This rank's addend goes to recv[slot][rank] of EVERY rank (own included) as 8-byte units
+            // {4 bytes of data, epoch}: vector (row, col) = two 16-byte stores {w0,e,w1,e} {w2,e,w3,e}, one per
+            // plane.  Consecutive lanes take consecutive units of the peer's block layout (norm_row.cuh), so a
+            // warp writes 512 contiguous bytes per store instruction.
+            named_bar_sync(2, 128);   // the four epilogue warps: the tile is staged
+            const int tid_e = (warp - 2) * 32 + lane, vpr = np >> 3, nvec_t = a.T * vpr;
+            const bool blocked = (np & 31) == 0;
+            const int per_blk = a.T * 4;
+            const int64_t base = a.push_recv_offset + slot_sel * a.push_slot_stride + a.push_rank * a.push_recv_stride;
+            for (int idx = tid_e; idx < nvec_t; idx += 128) {
+                int r_, vec;
+                if (blocked) {
+                    const int blk = idx / per_blk, rem = idx - blk * per_blk;
+                    r_ = rem >> 2;
+                    vec = blk * 4 + (rem & 3);
+                } else {
+                    r_ = idx / vpr;
+                    vec = idx - r_ * vpr;
+                }
+                const int col = p0 + vec * 8;
+                if (col >= J) continue;
+                const uint4 o = *reinterpret_cast<const uint4 *>(stg + (static_cast<size_t>(r_) * np + vec * 8) * sizeof(T));
+                const int64_t off = base + p2p_unit_offset(r_, col, a.T);
+#pragma unroll 1
+                for (int d = 0; d < a.push_world; ++d) {
+                    const int r = (a.push_rank + d) % a.push_world;
+                    unsigned char *dst = a.push_region[r] + off;
+                    st_relaxed_sys_v4(dst, o.x, epoch, o.y, epoch);
+                    st_relaxed_sys_v4(dst + a.push_plane_bytes, o.z, epoch, o.w, epoch);
+                }
+            }
+            named_bar_sync(2, 128);   // the staging buffer is free for the CTA's next tile
+        }
+    } else {
+        // paired tile: accumulator columns [0, np) = first half (rows p0.. of the group), [np, 2 np) =
+        // second half (the same rows `half_stride` further down)
+        const bool is_q = g < a.num_heads, is_k = !is_q && g < a.num_heads + a.num_kv_heads;
+        for (int c = 0; c < np; c += 8) {
+            uint32_t lo[8], hi[8];
+            load8(c, lo);
+            load8(np + c, hi);
+            tmem_ld_wait();
+            const int j0 = p0 + c;
+            if (j0 >= J || !row_ok) continue;
+            float f1[8], f2[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                f1[i] = round_io<T>(__uint_as_float(lo[i]));
+                f2[i] = round_io<T>(__uint_as_float(hi[i]));
+            }
+            if (EPI == kEpiSilu) {
+                // silu(gate) * up (llama.rs:364): fp32 on the model-dtype projections, one rounding
+                float o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = (f1[i] / (1.f + __expf(-f1[i]))) * f2[i];
+                store8<T>(y + j0, pack8<T>(o), J - j0, y_vec);
+            } else {
+                // RoPE (non-interleaved, candle_nn::rotary_emb::rope; llama.rs:218-251) on q and k heads;
+                // v heads pass through.  Same arithmetic as rope_reshape_and_cache_kernel.
+                float o1[8], o2[8];
+                if (is_q || is_k) {
+                    float fc[8], fs[8];
+                    unpack8<T>(*reinterpret_cast<const uint4 *>(cos_r + j0), fc);
+                    unpack8<T>(*reinterpret_cast<const uint4 *>(sin_r + j0), fs);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        o1[i] = __fmaf_rn(f1[i], fc[i], -__fmul_rn(f2[i], fs[i]));
+                        o2[i] = __fmaf_rn(f1[i], fs[i], __fmul_rn(f2[i], fc[i]));
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        o1[i] = f1[i];
+                        o2[i] = f2[i];
+                    }
+                }
+                const uint4 w1 = pack8<T>(o1), w2 = pack8<T>(o2);
+                T *dst = y + static_cast<int64_t>(g) * (2 * J) + j0;
+                store8<T>(dst, w1, J - j0, y_vec);
+                store8<T>(dst + J, w2, J - j0, y_vec);
+                if (!is_q && cache_row >= 0) {
+                    // reshape_and_cache_flash (cache_manager.cu:140-170): k_cache[slot / bs, slot % bs, head, :]
+                    T *cache = static_cast<T *>(is_k ? a.k_cache : a.v_cache);
+                    const int kvh = g - a.num_heads - (is_k ? 0 : a.num_kv_heads);
+                    T *cd = cache + cache_row + static_cast<int64_t>(kvh) * (2 * J) + j0;
+                    store8<T>(cd, w1, J - j0, true);
+                    store8<T>(cd + J, w2, J - j0, true);
+                }
+            }
+        }
+    }
+}
+
 template <typename T, int M, int EPI>
 __global__ void __launch_bounds__(kSkThreads, 1)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
@@ -306,31 +493,9 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         // ============================ epilogue warps (2..5) ============================
         pdl_wait();
         const int quad = warp & 3;   // the TMEM lane quadrant this warp may read
-        // M = 64: accumulator row r lives in lane (r % 16) + 32 (r / 16); M = 128: row r in lane r.
-        const int row = (M == 64) ? quad * 16 + lane : quad * 32 + lane;
-        const bool row_ok = (M == 64 ? lane < 16 : true) && row < a.T;
-        T *y = static_cast<T *>(a.y) + static_cast<int64_t>(row_ok ? row : 0) * a.ldy;
-        const bool y_vec = (a.ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0);
-        const int J = a.J, np = a.np;
-
-        // per-row constants of the fused epilogues
-        const T *cos_r = nullptr, *sin_r = nullptr;
-        int64_t cache_row = -1;
-        if (EPI == kEpiRope && row_ok) {
-            const int64_t pos = a.positions[row];
-            cos_r = static_cast<const T *>(a.cos) + pos * a.rot_stride;
-            sin_r = static_cast<const T *>(a.sin) + pos * a.rot_stride;
-            const int64_t slot = a.slot_mapping ? a.slot_mapping[row] : -1;   // < 0: padded token (cache_manager.cu:151-155)
-            if (slot >= 0 && a.k_cache)
-                cache_row = (slot / a.block_size) * a.block_stride + (slot % a.block_size) * a.num_kv_heads * (2 * J);
-        }
-        uint32_t epoch = 0;
-        int slot_sel = 0;
-        unsigned char *stg = ring + a.stages * a.stage_bytes + M * 128;   // push epilogue: [t_box][np] staging behind the ring
-        if (EPI == kEpiPush) {
-            epoch = a.push_state[0] + 1;   // this all-reduce's epoch (advanced by the receive-side kernel)
-            slot_sel = static_cast<int>(epoch & 1u);
-        }
+        const int np = a.np;
+        // push epilogue: [t_box][np] staging behind the ring
+        const EpiRow<T> er = epi_row_init<T, M, EPI>(a, warp, lane, ring + a.stages * a.stage_bytes + M * 128);
 
         for (int it = 0; it < my_tiles; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
@@ -340,133 +505,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
             tc_fence_after_sync();
             if (a.trace && tid == 64) a.trace[blockIdx.x * 8 + 2] = sk_timer_ns();
             const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * (a.nacc * a.acc_stride);
-            // 8 consecutive columns of the tile: the sum of the nacc partial accumulators (fixed order)
-            auto load8 = [&](int col, uint32_t (&v)[8]) {
-                tmem_ld_32x32b_x8(tacc + col, v);
-                for (int i = 1; i < a.nacc; ++i) {
-                    uint32_t w[8];
-                    tmem_ld_32x32b_x8(tacc + i * a.acc_stride + col, w);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
-                }
-            };
-
-            if (EPI == kEpiPlain || EPI == kEpiPush) {
-                // columns [p0, p0 + np) of the output, 8 at a time, two TMEM loads in flight
-                for (int c = 0; c < np; c += 16) {
-                    uint32_t v0[8], v1[8];
-                    load8(c, v0);
-                    if (c + 8 < np) load8(c + 8, v1);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int j0 = p0 + c + 8 * u;
-                        if (c + 8 * u >= np || j0 >= J || !row_ok) continue;
-                        float f[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(u == 0 ? v0[i] : v1[i]);
-                        const uint4 o = pack8<T>(f);
-                        if (EPI == kEpiPlain) {
-                            store8<T>(y + j0, o, J - j0, y_vec);
-                        } else {
-                            // tensor parallel: stage the tile in shared memory; pushed below, coalesced
-                            *reinterpret_cast<uint4 *>(stg + (static_cast<size_t>(row) * np + c + 8 * u) * sizeof(T)) = o;
-                        }
-                    }
-                }
-                if (EPI == kEpiPush) {
-                    // This rank's addend goes to recv[slot][rank] of EVERY rank (own included) as 8-byte units
-                    // {4 bytes of data, epoch}: vector (row, col) = two 16-byte stores {w0,e,w1,e} {w2,e,w3,e}, one per
-                    // plane.  Consecutive lanes take consecutive units of the peer's block layout (norm_row.cuh), so a
-                    // warp writes 512 contiguous bytes per store instruction.
-                    named_bar_sync(2, 128);   // the four epilogue warps: the tile is staged
-                    const int tid_e = (warp - 2) * 32 + lane, vpr = np >> 3, nvec_t = a.T * vpr;
-                    const bool blocked = (np & 31) == 0;
-                    const int per_blk = a.T * 4;
-                    const int64_t base = a.push_recv_offset + slot_sel * a.push_slot_stride + a.push_rank * a.push_recv_stride;
-                    for (int idx = tid_e; idx < nvec_t; idx += 128) {
-                        int r_, vec;
-                        if (blocked) {
-                            const int blk = idx / per_blk, rem = idx - blk * per_blk;
-                            r_ = rem >> 2;
-                            vec = blk * 4 + (rem & 3);
-                        } else {
-                            r_ = idx / vpr;
-                            vec = idx - r_ * vpr;
-                        }
-                        const int col = p0 + vec * 8;
-                        if (col >= J) continue;
-                        const uint4 o = *reinterpret_cast<const uint4 *>(stg + (static_cast<size_t>(r_) * np + vec * 8) * sizeof(T));
-                        const int64_t off = base + p2p_unit_offset(r_, col, a.T);
-#pragma unroll 1
-                        for (int d = 0; d < a.push_world; ++d) {
-                            const int r = (a.push_rank + d) % a.push_world;
-                            unsigned char *dst = a.push_region[r] + off;
-                            st_relaxed_sys_v4(dst, o.x, epoch, o.y, epoch);
-                            st_relaxed_sys_v4(dst + a.push_plane_bytes, o.z, epoch, o.w, epoch);
-                        }
-                    }
-                    named_bar_sync(2, 128);   // the staging buffer is free for the CTA's next tile
-                }
-            } else {
-                // paired tile: accumulator columns [0, np) = first half (rows p0.. of the group), [np, 2 np) =
-                // second half (the same rows `half_stride` further down)
-                const bool is_q = g < a.num_heads, is_k = !is_q && g < a.num_heads + a.num_kv_heads;
-                for (int c = 0; c < np; c += 8) {
-                    uint32_t lo[8], hi[8];
-                    load8(c, lo);
-                    load8(np + c, hi);
-                    tmem_ld_wait();
-                    const int j0 = p0 + c;
-                    if (j0 >= J || !row_ok) continue;
-                    float f1[8], f2[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        f1[i] = round_io<T>(__uint_as_float(lo[i]));
-                        f2[i] = round_io<T>(__uint_as_float(hi[i]));
-                    }
-                    if (EPI == kEpiSilu) {
-                        // silu(gate) * up (llama.rs:364): fp32 on the model-dtype projections, one rounding
-                        float o[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) o[i] = (f1[i] / (1.f + __expf(-f1[i]))) * f2[i];
-                        store8<T>(y + j0, pack8<T>(o), J - j0, y_vec);
-                    } else {
-                        // RoPE (non-interleaved, candle_nn::rotary_emb::rope; llama.rs:218-251) on q and k heads;
-                        // v heads pass through.  Same arithmetic as rope_reshape_and_cache_kernel.
-                        float o1[8], o2[8];
-                        if (is_q || is_k) {
-                            float fc[8], fs[8];
-                            unpack8<T>(*reinterpret_cast<const uint4 *>(cos_r + j0), fc);
-                            unpack8<T>(*reinterpret_cast<const uint4 *>(sin_r + j0), fs);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                o1[i] = __fmaf_rn(f1[i], fc[i], -__fmul_rn(f2[i], fs[i]));
-                                o2[i] = __fmaf_rn(f1[i], fs[i], __fmul_rn(f2[i], fc[i]));
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                o1[i] = f1[i];
-                                o2[i] = f2[i];
-                            }
-                        }
-                        const uint4 w1 = pack8<T>(o1), w2 = pack8<T>(o2);
-                        T *dst = y + static_cast<int64_t>(g) * (2 * J) + j0;
-                        store8<T>(dst, w1, J - j0, y_vec);
-                        store8<T>(dst + J, w2, J - j0, y_vec);
-                        if (!is_q && cache_row >= 0) {
-                            // reshape_and_cache_flash (cache_manager.cu:140-170): k_cache[slot / bs, slot % bs, head, :]
-                            T *cache = static_cast<T *>(is_k ? a.k_cache : a.v_cache);
-                            const int kvh = g - a.num_heads - (is_k ? 0 : a.num_kv_heads);
-                            T *cd = cache + cache_row + static_cast<int64_t>(kvh) * (2 * J) + j0;
-                            store8<T>(cd, w1, J - j0, true);
-                            store8<T>(cd + J, w2, J - j0, true);
-                        }
-                    }
-                }
-            }
+            epilogue_tile<T, M, EPI>(a, er, tacc, g, p0, warp, lane);
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[buf]);
@@ -535,6 +574,196 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
                 }
             }
         }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Two projections chained in ONE kernel: y1 = epi1( silu_mul(x0 . W0^T) . W1^T )  — the MLP of a Llama block
+// (gate_up + SwiGLU, then down_proj; models/src/llama.rs:362-366).
+//
+// Why: the step timeline (scripts/trace_step.py, per-SM hand-over) shows that an SM whose CTA used tensor memory
+// takes 3.3 us (32 accumulator columns) to 12 us (208 columns: gate_up) to accept the next kernel's CTA, against
+// 0.5 us after the decode-attention kernel, which uses none — and down_proj's CTAs need exactly the SMs gate_up's
+// CTAs leave.  Here the CTA stays: phase 1 keeps the ring, the barriers and the tensor-memory allocation of phase 0,
+// its weights start streaming into the ring as phase 0's last stages drain, and the only dependency is a grid-wide
+// arrival counter ("every CTA has stored its slice of the activations") that gates phase 1's x loads alone.
+// Both phases: one tile per CTA (single wave), common ring geometry (stage size = the larger of the two).
+struct ChainArgs {
+    SkinnyArgs p[2];
+    uint32_t *sync;     // [2] zero between launches: phase-0 tiles stored, phase-1 x producers released
+    int stages, stage_bytes, tmem_cols;
+    int tmem_col1;      // first accumulator column of phase 1 (phase 0 starts at 0)
+};
+
+template <typename T, int M, int EPI1>
+__global__ void __launch_bounds__(kSkThreads, 1)
+gemm_chain2_kernel(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_x0,
+                   const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_x1,
+                   const ChainArgs c) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *ring = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    __shared__ __align__(8) uint64_t full[kSkMaxStages], empty[kSkMaxStages], tfull[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const SkinnyArgs &a0 = c.p[0], &a1 = c.p[1];
+    const unsigned long long t_start = a0.trace ? sk_timer_ns() : 0ull;
+    if (tid == 0) {
+        for (int i = 0; i < c.stages; ++i) {
+            mbar_init(&full[i], 2);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(&tfull[0], 1);
+        mbar_init(&tfull[1], 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&map_w0);
+        tma_prefetch_desc(&map_x0);
+        tma_prefetch_desc(&map_w1);
+        tma_prefetch_desc(&map_x1);
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tmem_alloc(&tmem_base_smem, c.tmem_cols);
+        tc_fence_before_sync();
+    }
+    if (warp >= 1 && warp <= 5) {
+        named_bar_sync(1, 5 * 32);
+        tc_fence_after_sync();
+    }
+    const uint32_t tmem_base = (warp >= 1 && warp <= 5) ? tmem_base_smem : 0u;
+    const int b = static_cast<int>(blockIdx.x);
+    const bool has0 = b < a0.tiles, has1 = b < a1.tiles;   // one tile per CTA and phase
+
+    if (warp == 0 || warp == 7) {
+        // ============================ TMA producers (warp 0: W, warp 7: x) ============================
+        const bool is_w = warp == 0;
+        if (is_w) pdl_launch_dependents();
+        if (!(is_w && a0.prefetch_w)) pdl_wait();   // weights are immutable: they stream ahead of the grid dependency
+        if (a0.trace && !is_w && lane == 0) a0.trace[b * 8 + 6] = sk_timer_ns();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int ph = 0; ph < 2; ++ph) {
+            const SkinnyArgs &a = ph == 0 ? a0 : a1;
+            if (!(ph == 0 ? has0 : has1)) continue;
+            const CUtensorMap *mw = ph == 0 ? &map_w0 : &map_w1, *mx = ph == 0 ? &map_x0 : &map_x1;
+            const int g = b / a.tiles_per_group, p0 = (b - g * a.tiles_per_group) * a.np;
+            if (ph == 1 && !is_w) {
+                // phase 1 reads what EVERY CTA stored in phase 0: wait for all of them, then order the generic-proxy
+                // stores (made visible by the acquire) before this thread's async-proxy (TMA) reads
+                if (lane == 0) {
+                    while (ld_acquire_gpu_u32(&c.sync[0]) < static_cast<uint32_t>(a0.tiles)) __nanosleep(32);
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    if (atomicAdd(&c.sync[1], 1u) == static_cast<uint32_t>(a1.tiles - 1)) {   // last reader: reset for the next launch
+                        c.sync[0] = 0;
+                        c.sync[1] = 0;
+                    }
+                }
+                __syncwarp();
+                if (a1.trace && lane == 0) a1.trace[b * 8 + 6] = sk_timer_ns();
+            }
+            for (int ch = 0; ch < a.chunks; ++ch) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                unsigned char *dst = ring + stage * c.stage_bytes;
+                if (a.trace && is_w && lane == 0 && ch == 0) {
+                    unsigned smid;
+                    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                    a.trace[b * 8 + 4] = smid;
+                    a.trace[b * 8 + 0] = ph == 0 ? t_start : sk_timer_ns();
+                }
+                if (elect_one_sync()) {
+                    if (is_w) {
+                        mbar_arrive_expect_tx(&full[stage], a.w_bytes);
+                        tma_load_5d(dst, mw, &full[stage], 0, p0, 0, ch * a.kbs, g, kL2EvictFirst);
+                    } else {
+                        mbar_arrive_expect_tx(&full[stage], a.x_bytes);
+                        tma_load_3d(dst + a.w_bytes, mx, &full[stage], 0, 0, ch * a.kbs, kL2EvictLast);
+                    }
+                }
+                __syncwarp();
+                if (++stage == c.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+        if (is_w && a0.prefetch_w) pdl_wait();
+    } else if (warp == 1) {
+        // ============================ MMA issuer ============================
+        pdl_wait();
+        const uint32_t ring_u32 = smem_u32(ring);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int ph = 0; ph < 2; ++ph) {
+            const SkinnyArgs &a = ph == 0 ? a0 : a1;
+            if (!(ph == 0 ? has0 : has1)) continue;
+            const uint32_t idesc = umma_idesc_f16(M, a.n_tile, a.is_bf16 != 0);
+            const int w_slab = a.n_tile * 128, x_slab = a.t_box * 128;
+            const uint32_t tmem_d = tmem_base + (ph == 0 ? 0 : c.tmem_col1);
+            int step = 0;
+            for (int ch = 0; ch < a.chunks; ++ch) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after_sync();
+                if (a.trace && ch == 0 && lane == 0) a.trace[b * 8 + 1] = sk_timer_ns();
+                if (a.trace && ch == a.chunks - 1 && lane == 0) a.trace[b * 8 + 7] = sk_timer_ns();
+                const uint32_t base = ring_u32 + stage * c.stage_bytes;
+                const int nkb = min(a.kbs, a.kb_total - ch * a.kbs);
+                if (elect_one_sync()) {
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        const uint64_t da = umma_desc_k_sw128(base + a.w_bytes + kb * x_slab);
+                        const uint64_t db = umma_desc_k_sw128(base + kb * w_slab);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (step + kb * 4 + k) > 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);
+                }
+                __syncwarp();
+                step += nkb * 4;
+                if (++stage == c.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            if (elect_one_sync()) umma_commit(&tfull[ph]);
+            __syncwarp();
+        }
+    } else if (warp >= 2 && warp <= 5) {
+        // ============================ epilogue warps ============================
+        pdl_wait();
+        const int quad = warp & 3;
+        unsigned char *stg = ring + c.stages * c.stage_bytes + M * 128;
+        if (has0) {
+            const EpiRow<T> er = epi_row_init<T, M, kEpiSilu>(a0, warp, lane, stg);
+            const int g = b / a0.tiles_per_group, p0 = (b - g * a0.tiles_per_group) * a0.np;
+            mbar_wait(&tfull[0], 0);
+            tc_fence_after_sync();
+            if (a0.trace && tid == 64) a0.trace[b * 8 + 2] = sk_timer_ns();
+            epilogue_tile<T, M, kEpiSilu>(a0, er, tmem_base + (static_cast<uint32_t>(quad * 32) << 16), g, p0, warp, lane);
+            // this CTA's slice of the activations is stored: publish it to every CTA's phase-1 x producer
+            __threadfence();
+            named_bar_sync(2, 128);
+            if (tid == 64) {
+                atomicAdd(&c.sync[0], 1u);
+                if (a0.trace) a0.trace[b * 8 + 3] = sk_timer_ns();
+            }
+        }
+        if (has1) {
+            const EpiRow<T> er = epi_row_init<T, M, EPI1>(a1, warp, lane, stg);
+            const int g = b / a1.tiles_per_group, p0 = (b - g * a1.tiles_per_group) * a1.np;
+            mbar_wait(&tfull[1], 0);
+            tc_fence_after_sync();
+            if (a1.trace && tid == 64) a1.trace[b * 8 + 2] = sk_timer_ns();
+            epilogue_tile<T, M, EPI1>(a1, er, tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c.tmem_col1, g, p0, warp, lane);
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (a1.trace && tid == 0 && has1) a1.trace[b * 8 + 3] = sk_timer_ns();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, c.tmem_cols);
     }
 }
 
@@ -793,6 +1022,141 @@ bool launch_skinny_gemm(SkinnyArgs a, const void *x, const void *w, int T, int64
         return false;
     }
     return check_launch("gemm_skinny_kernel");
+}
+
+// ---- chained MLP (gemm_chain2_kernel) ----
+namespace {
+
+// Tiling of one phase of a chain: the single-kernel rules of launch_skinny_gemm (tile width from choose_np, as many k
+// blocks per stage as fit `stage_cap`), without the diagnostics overrides.
+void plan_chain_phase(SkinnyArgs &a, int T, int64_t K, int G, int J, int halves, int stage_cap, int sms, bool is_bf16) {
+    a.T = T;
+    a.m = T <= 64 ? 64 : 128;
+    a.t_box = (T + 7) / 8 * 8;
+    a.kb_total = static_cast<int>(K / 64);
+    a.J = J;
+    a.G = G;
+    a.halves = halves;
+    a.np = choose_np(G, J, halves, sms);
+    a.n_tile = a.np * halves;
+    a.tiles_per_group = (J + a.np - 1) / a.np;
+    a.tiles = G * a.tiles_per_group;
+    const int per_kb = (a.n_tile + a.t_box) * 128;
+    int kbs = 16;
+    while (kbs > 1 && (kbs * per_kb > stage_cap || kbs > a.kb_total)) kbs >>= 1;
+    a.kbs = kbs;
+    a.w_ops = 1;
+    a.wkb = kbs;
+    a.chunks = (a.kb_total + kbs - 1) / kbs;
+    a.w_bytes = kbs * a.n_tile * 128;
+    a.x_bytes = kbs * a.t_box * 128;
+    a.stage_bytes = a.w_bytes + a.x_bytes;
+    a.acc_stride = (a.n_tile + 31) / 32 * 32;
+    a.nacc = 1;
+    a.nbuf = 1;
+    a.is_bf16 = is_bf16 ? 1 : 0;
+    a.prefetch_w = ((launch_flags() & (kLaunchPdl | kLaunchConstWeights)) == (kLaunchPdl | kLaunchConstWeights)) ? 1 : 0;
+}
+
+template <typename T, int M>
+cudaError_t launch_chain_epi(int epi1, dim3 grid, size_t smem, cudaStream_t stream, const CUtensorMap &mw0, const CUtensorMap &mx0,
+                             const CUtensorMap &mw1, const CUtensorMap &mx1, const ChainArgs &c) {
+    static thread_local int attr_dev = -1;
+    const DeviceInfo &di = current_device_info();
+    if (attr_dev != di.ordinal) {
+        const int lim = kSkSmemBudget + 128 * 128 + 1024;   // ring + staging <= budget, + operand slack + alignment
+        cudaError_t e = cudaSuccess;
+        auto set = [&](auto *k) {
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        };
+        set(gemm_chain2_kernel<T, M, kEpiPlain>);
+        set(gemm_chain2_kernel<T, M, kEpiPush>);
+        if (e != cudaSuccess) return e;
+        attr_dev = di.ordinal;
+    }
+    if (epi1 == kEpiPush)
+        return launch_ex(gemm_chain2_kernel<T, M, kEpiPush>, grid, dim3(kSkThreads), smem, stream, mw0, mx0, mw1, mx1, c);
+    return launch_ex(gemm_chain2_kernel<T, M, kEpiPlain>, grid, dim3(kSkThreads), smem, stream, mw0, mx0, mw1, mx1, c);
+}
+
+bool make_phase_maps(CUtensorMap *mw, CUtensorMap *mx, const SkinnyArgs &a, const void *x, const void *w, int64_t ldx, int64_t ldw,
+                     int64_t half_stride_rows, bool is_bf16) {
+    const uint64_t wd[5] = {64, static_cast<uint64_t>(a.J), static_cast<uint64_t>(a.halves), static_cast<uint64_t>(a.kb_total), 1};
+    const uint64_t row_b = static_cast<uint64_t>(ldw) * 2;
+    const uint64_t ws[4] = {row_b, a.halves > 1 ? static_cast<uint64_t>(half_stride_rows) * row_b : row_b, 128, row_b};
+    const uint32_t wb[5] = {64, static_cast<uint32_t>(a.np), static_cast<uint32_t>(a.halves), static_cast<uint32_t>(a.kbs), 1};
+    if (!make_tiled_map(mw, w, 5, wd, ws, wb, is_bf16)) return false;
+    const uint64_t xd[3] = {64, static_cast<uint64_t>(a.T), static_cast<uint64_t>(a.kb_total)};
+    const uint64_t xs[2] = {static_cast<uint64_t>(ldx) * 2, 128};
+    const uint32_t xb[3] = {64, static_cast<uint32_t>(a.t_box), static_cast<uint32_t>(a.kbs)};
+    return make_tiled_map(mx, x, 3, xd, xs, xb, is_bf16);
+}
+
+}  // namespace
+
+int g_sk_chain_mlp = 1;   // atoma_debug_step_fusion bit 1: 0 = gate_up and down_proj as two kernels
+void set_skinny_chain(int on) { g_sk_chain_mlp = on ? 1 : 0; }
+
+// act[T, inter] = silu(x Wg^T) * (x Wu^T) (stored, as the unchained pair does), then `a1.epi` (plain into a1.y, or
+// push) of act . Wdown^T, in one launch.  Returns 0 when the shapes do not qualify (the caller launches the two
+// kernels), 1 when launched, -1 on error.
+int try_launch_mlp_chain(const void *x, const void *w_gate_up, void *act, const void *w_down, SkinnyArgs a1, int T, int64_t inter,
+                         int64_t hidden, int64_t ldx, int64_t ldw_gu, int64_t ld_act, int64_t ldw_down, bool is_bf16,
+                         cudaStream_t stream) {
+    const DeviceInfo &di = current_device_info();
+    if (!g_sk_chain_mlp || g_sk_trace || g_sk_force_np || g_sk_force_kbs || g_sk_stage_limit || g_sk_budget_kib || g_sk_debug_skip ||
+        !(launch_flags() & kLaunchPdl))
+        return 0;
+    if (!skinny_gemm_supported(T, hidden, ldx, ldw_gu) || !skinny_gemm_supported(T, inter, ld_act, ldw_down) || inter % 8) return 0;
+    constexpr int kStageCap = 64 * 1024;
+    ChainArgs c{};
+    SkinnyArgs &a0 = c.p[0];
+    a0.epi = kEpiSilu;
+    a0.y = act;
+    a0.ldy = ld_act;
+    plan_chain_phase(a0, T, hidden, 1, static_cast<int>(inter), 2, kStageCap, di.sm_count, is_bf16);
+    c.p[1] = a1;
+    SkinnyArgs &p1 = c.p[1];
+    plan_chain_phase(p1, T, inter, 1, static_cast<int>(hidden), 1, kStageCap, di.sm_count, is_bf16);
+    if (a0.tiles > di.sm_count || p1.tiles > di.sm_count) return 0;   // single wave only
+    c.stage_bytes = std::max(a0.stage_bytes, p1.stage_bytes);
+    const int stg_bytes = p1.epi == kEpiPush ? p1.t_box * p1.n_tile * 2 : 0;
+    c.stages = std::min(kSkMaxStages, (kSkSmemBudget - stg_bytes) / c.stage_bytes);
+    if (c.stages < 2) return 0;
+    a0.stages = p1.stages = c.stages;
+    a0.stage_bytes = p1.stage_bytes = c.stage_bytes;
+    c.tmem_col1 = a0.acc_stride;
+    int cols = 32;
+    while (cols < a0.acc_stride + p1.acc_stride) cols <<= 1;
+    if (cols > 512) return 0;
+    c.tmem_cols = cols;
+    a0.tmem_cols = p1.tmem_cols = cols;
+    c.sync = static_cast<uint32_t *>(get_workspace(stream, 256, kWorkspaceSkinnyTail));
+    if (!c.sync) return -1;
+    c.sync += 8;   // words 8, 9 of the tail workspace (0, 1 belong to the fused norm tail)
+    a0.trace = next_step_trace_slot("chain gate_up+silu");
+    p1.trace = next_step_trace_slot(p1.epi == kEpiPush ? "chain down push" : "chain down");
+    take_next_kernel_prefetch();   // hints are not used by the chain
+    CUtensorMap mw0, mx0, mw1, mx1;
+    if (!make_phase_maps(&mw0, &mx0, a0, x, w_gate_up, ldx, ldw_gu, inter, is_bf16)) return -1;
+    if (!make_phase_maps(&mw1, &mx1, p1, act, w_down, ld_act, ldw_down, 0, is_bf16)) return -1;
+    const int grid = std::max(a0.tiles, p1.tiles);
+    const size_t smem = static_cast<size_t>(c.stages) * c.stage_bytes + a0.m * 128 + 1024 + stg_bytes;
+    cudaError_t e;
+    if (is_bf16) {
+        e = a0.m == 64 ? launch_chain_epi<__nv_bfloat16, 64>(p1.epi, dim3(grid), smem, stream, mw0, mx0, mw1, mx1, c)
+                       : launch_chain_epi<__nv_bfloat16, 128>(p1.epi, dim3(grid), smem, stream, mw0, mx0, mw1, mx1, c);
+    } else {
+        e = a0.m == 64 ? launch_chain_epi<__half, 64>(p1.epi, dim3(grid), smem, stream, mw0, mx0, mw1, mx1, c)
+                       : launch_chain_epi<__half, 128>(p1.epi, dim3(grid), smem, stream, mw0, mx0, mw1, mx1, c);
+    }
+    note_launch();
+    if (e != cudaSuccess) {
+        set_status(static_cast<int>(e), "gemm_chain2_kernel: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    return check_launch("gemm_chain2_kernel") ? 1 : -1;
 }
 
 }  // namespace atoma

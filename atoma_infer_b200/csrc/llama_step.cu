@@ -175,6 +175,16 @@ bool gate_up_silu(const void *x, const void *w, void *y, int64_t T, int64_t inte
     return true;
 }
 
+void fill_push_args(SkinnyArgs &a, void *const *regions, int rank, int world, int64_t slot_bytes, int64_t T, int64_t N) {
+    a.epi = kEpiPush;
+    for (int r = 0; r < 8; ++r) a.push_region[r] = static_cast<unsigned char *>(regions[r < world ? r : rank]);
+    a.push_state = reinterpret_cast<const uint32_t *>(regions[rank]);
+    p2p_layout(slot_bytes, &a.push_recv_offset, &a.push_slot_stride, &a.push_recv_stride);
+    a.push_plane_bytes = T * N * 2;
+    a.push_rank = rank;
+    a.push_world = world;
+}
+
 bool gemm_tn_push(const void *x, const void *w, int64_t T, int64_t N, int64_t K, int64_t ldx, int64_t ldw,
                   void *const *regions, int rank, int world, int64_t slot_bytes, uint32_t dtype, cudaStream_t stream,
                   const NormArgs *tail = nullptr) {
@@ -193,13 +203,7 @@ bool gemm_tn_push(const void *x, const void *w, int64_t T, int64_t N, int64_t K,
         return false;
     }
     SkinnyArgs a{};
-    a.epi = kEpiPush;
-    for (int r = 0; r < 8; ++r) a.push_region[r] = static_cast<unsigned char *>(regions[r < world ? r : rank]);
-    a.push_state = reinterpret_cast<const uint32_t *>(regions[rank]);
-    p2p_layout(slot_bytes, &a.push_recv_offset, &a.push_slot_stride, &a.push_recv_stride);
-    a.push_plane_bytes = T * N * 2;
-    a.push_rank = rank;
-    a.push_world = world;
+    fill_push_args(a, regions, rank, world, slot_bytes, T, N);
     if (tail) {   // receive side (the all-reduce's sum + residual + RMSNorm) in the same kernel
         a.norm_tail = 1;
         a.norm = *tail;
@@ -468,29 +472,46 @@ extern "C" void atoma_llama_decode_step(const atoma_llama_model *model, const at
                                     nullptr, 0, 1, stream))
                 return;
         }
-        // MLP: silu(gate) * up, down  (llama.rs:362-366)
-        hint(4, ly.w_down, hid * m.inter * 2);
-        if (!gate_up_silu(s.normed, ly.w_gate_up, s.act, T, m.inter, hid, hid, hid, m.inter, dt, stream)) return;
-        if (l + 1 < m.num_layers) hint(8, m.layers[l + 1].wqkv, nqkv * hid * 2);
-        else if (m.lm_head) hint(8, m.lm_head, m.vocab * hid * 2);
-        if (fuse) {
-            // x = mlp + residual, then the NEXT block's rms_1 — or ln_f after the last block  (llama.rs:408, 399, 474)
-            const bool last = l + 1 == m.num_layers;
-            const NormArgs tail_next = norm_tail_args(s.resid, last ? nullptr : s.resid, last ? m.norm_f : m.layers[l + 1].rms_attn,
-                                                      last ? final_normed : s.normed, T, hid, hid, hid, hid, m.rms_eps);
+        // MLP: silu(gate) * up, down  (llama.rs:362-366) — ONE kernel when the shapes allow (gemm_chain2_kernel)
+        int chained = 0;
+        if (!fuse && hid % 32 == 0) {
+            SkinnyArgs a1{};
             if (world > 1) {
+                fill_push_args(a1, m.p2p_regions, m.tp_rank, world, m.p2p_slot_bytes, T, hid);
+            } else {
+                a1.epi = kEpiPlain;
+                a1.y = s.proj;
+                a1.ldy = hid;
+            }
+            chained = try_launch_mlp_chain(s.normed, ly.w_gate_up, s.act, ly.w_down, a1, static_cast<int>(T), m.inter, hid, hid, hid,
+                                           m.inter, m.inter, dt == 1, stream);
+            if (chained < 0) return;
+        }
+        if (!chained) {
+            hint(4, ly.w_down, hid * m.inter * 2);
+            if (!gate_up_silu(s.normed, ly.w_gate_up, s.act, T, m.inter, hid, hid, hid, m.inter, dt, stream)) return;
+            if (l + 1 < m.num_layers) hint(8, m.layers[l + 1].wqkv, nqkv * hid * 2);
+            else if (m.lm_head) hint(8, m.lm_head, m.vocab * hid * 2);
+            if (fuse) {
+                // x = mlp + residual, then the NEXT block's rms_1 — or ln_f after the last block  (llama.rs:408, 399, 474)
+                const bool last = l + 1 == m.num_layers;
+                const NormArgs tail_next = norm_tail_args(s.resid, last ? nullptr : s.resid, last ? m.norm_f : m.layers[l + 1].rms_attn,
+                                                          last ? final_normed : s.normed, T, hid, hid, hid, hid, m.rms_eps);
+                if (world > 1) {
+                    if (!gemm_tn_push(s.act, ly.w_down, T, hid, m.inter, m.inter, m.inter, m.p2p_regions, m.tp_rank, world,
+                                      m.p2p_slot_bytes, dt, stream, &tail_next))
+                        return;
+                } else {
+                    if (!gemm_tn(s.act, ly.w_down, s.proj, T, hid, m.inter, m.inter, m.inter, hid, dt, stream, &tail_next)) return;
+                }
+            } else if (world > 1) {
                 if (!gemm_tn_push(s.act, ly.w_down, T, hid, m.inter, m.inter, m.inter, m.p2p_regions, m.tp_rank, world,
-                                  m.p2p_slot_bytes, dt, stream, &tail_next))
+                                  m.p2p_slot_bytes, dt, stream))
                     return;
             } else {
-                if (!gemm_tn(s.act, ly.w_down, s.proj, T, hid, m.inter, m.inter, m.inter, hid, dt, stream, &tail_next)) return;
+                if (!gemm_tn(s.act, ly.w_down, s.proj, T, hid, m.inter, m.inter, m.inter, hid, dt, stream)) return;
             }
-        } else if (world > 1) {
-            if (!gemm_tn_push(s.act, ly.w_down, T, hid, m.inter, m.inter, m.inter, m.p2p_regions, m.tp_rank, world,
-                              m.p2p_slot_bytes, dt, stream))
-                return;
-        } else {
-            if (!gemm_tn(s.act, ly.w_down, s.proj, T, hid, m.inter, m.inter, m.inter, hid, dt, stream)) return;
+    
         }
     }
     // x = mlp + residual; ln_f  (llama.rs:408, 474)
@@ -526,7 +547,35 @@ extern "C" void atoma_debug_skinny_trace(void *device_buf) { set_skinny_trace(de
 extern "C" void atoma_debug_skinny_tuning(int np, int kbs, int stages) { set_skinny_tuning(np, kbs, stages); }
 extern "C" void atoma_debug_skinny_mode(int skip_loads, int w_ops) { set_skinny_debug(skip_loads, w_ops); }
 extern "C" void atoma_debug_skinny_budget(int kib) { set_skinny_budget(kib); }
-extern "C" void atoma_debug_step_fusion(int norm_tail) { g_step_norm_tail = norm_tail ? 1 : 0; }
+extern "C" void atoma_mlp_gate_up_down(const void *x, const void *w_gate_up, void *act, const void *w_down, void *y, int64_t T,
+                                       int64_t inter, int64_t hidden, int64_t ldx, int64_t ldw_gate_up, int64_t ld_act,
+                                       int64_t ldw_down, int64_t ldy, uint32_t dtype, atoma_stream_t stream_) {
+    clear_status();
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (T <= 0) return;
+    if (dtype > 1 || !x || !w_gate_up || !act || !w_down || !y || !al16(x) || !al16(w_gate_up) || !al16(act) || !al16(w_down) ||
+        !al16(y) || ldx % 8 || ldw_gate_up % 8 || ld_act % 8 || ldw_down % 8 || ldy % 8 || inter % 8 || ldx < hidden ||
+        ldw_gate_up < hidden || ld_act < inter || ldw_down < inter || ldy < hidden) {
+        set_status(kErrInvalidArg, "atoma_mlp_gate_up_down: 16-bit dtype, inter a multiple of 8, 16-byte aligned pointers and strides");
+        return;
+    }
+    if (T <= 128) {
+        SkinnyArgs a1{};
+        a1.epi = kEpiPlain;
+        a1.y = y;
+        a1.ldy = ldy;
+        const int r = try_launch_mlp_chain(x, w_gate_up, act, w_down, a1, static_cast<int>(T), inter, hidden, ldx, ldw_gate_up, ld_act,
+                                           ldw_down, dtype == 1, stream);
+        if (r != 0) return;
+    }
+    if (!gate_up_silu(x, w_gate_up, act, T, inter, hidden, ldx, ldw_gate_up, ld_act, dtype, stream)) return;
+    gemm_tn(act, w_down, y, T, hidden, inter, ld_act, ldw_down, ldy, dtype, stream);
+}
+
+extern "C" void atoma_debug_step_fusion(int flags) {
+    g_step_norm_tail = (flags & 1) ? 1 : 0;
+    set_skinny_chain((flags & 2) ? 0 : 1);   // bit 1 set: gate_up and down_proj as two kernels
+}
 
 extern "C" void atoma_gemm_tn_add_rmsnorm(const void *x, const void *w, void *y, int64_t T, int64_t N, int64_t K, int64_t ldx,
                                           int64_t ldw, int64_t ldy, const void *residual, void *residual_out,

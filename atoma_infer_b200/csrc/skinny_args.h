@@ -72,5 +72,12 @@ void set_skinny_trace(void *device_buf);
 void set_skinny_tuning(int np, int kbs, int stages);
 void set_skinny_debug(int skip, int w_ops);
 void set_skinny_budget(int kib);
+void set_skinny_chain(int on);
+// gate_up + SwiGLU and down_proj chained in ONE kernel (gemm_skinny.cu: gemm_chain2_kernel).  `a1`: the epilogue fields of
+// the second projection (epi = kEpiPlain with y / ldy, or kEpiPush with the push_* fields).  0 = shapes do not qualify
+// (launch the two kernels), 1 = launched, -1 = error.
+int try_launch_mlp_chain(const void *x, const void *w_gate_up, void *act, const void *w_down, SkinnyArgs a1, int T, int64_t inter,
+                         int64_t hidden, int64_t ldx, int64_t ldw_gu, int64_t ld_act, int64_t ldw_down, bool is_bf16,
+                         cudaStream_t stream);
 
 }  // namespace atoma

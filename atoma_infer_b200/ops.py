@@ -423,6 +423,21 @@ def add_rmsnorm(x, residual, weight, eps: float, residual_out=None, normed=None)
     return residual_out, normed
 
 
+def mlp_gate_up_down(x, w_gate_up, w_down, act=None, out=None):
+    """`Mlp::forward` (llama.rs:362-366): down(silu(gate(x)) * up(x)) -> (y, act); one kernel when it qualifies."""
+    T, hidden = x.shape
+    inter = w_gate_up.shape[0] // 2
+    if act is None:
+        act = torch.empty((T, inter), dtype=x.dtype, device=x.device)
+    if out is None:
+        out = torch.empty((T, w_down.shape[0]), dtype=x.dtype, device=x.device)
+    _lib.lib().atoma_mlp_gate_up_down(x.data_ptr(), w_gate_up.data_ptr(), act.data_ptr(), w_down.data_ptr(), out.data_ptr(), T, inter,
+                                      hidden, x.stride(0), w_gate_up.stride(0), act.stride(0), w_down.stride(0), out.stride(0),
+                                      _dt(x), _stream())
+    _raise_on_status()
+    return out, act
+
+
 def gemm_tn_add_rmsnorm(x, w, residual, weight, eps: float, out=None, residual_out=None, normed=None):
     """y = x w^T; h = y + residual; normed = rmsnorm(h) * weight — one kernel (llama.rs:311 + 401-407).  Returns
     (y, h, normed); bit-identical to gemm_tn followed by add_rmsnorm."""

@@ -65,6 +65,17 @@ void atoma_gate_up_silu(const void *x, const void *w_gate_up, void *y, int64_t T
                         int64_t ldx, int64_t ldw, int64_t ldy, uint32_t dtype, atoma_stream_t stream);
 
 /*
+ * The MLP of a block (llama.rs:362-366): act[T, inter] = silu(x w_gate^T) * (x w_up^T) and y[T, hidden] = act w_down^T.
+ * With programmatic dependent launch enabled, T <= 128 and one wave of tiles per projection both run in ONE kernel
+ * (gemm_chain2_kernel: the CTAs keep their ring, barriers and tensor memory across the two projections and the second
+ * one's weights start streaming while the first drains; a grid-wide arrival counter gates only its activation loads)
+ * — bit-identical to atoma_gate_up_silu + atoma_gemm_tn, which is what runs otherwise.  act is written either way.
+ */
+void atoma_mlp_gate_up_down(const void *x, const void *w_gate_up, void *act, const void *w_down, void *y, int64_t T,
+                            int64_t inter, int64_t hidden, int64_t ldx, int64_t ldw_gate_up, int64_t ld_act,
+                            int64_t ldw_down, int64_t ldy, uint32_t dtype, atoma_stream_t stream);
+
+/*
  * Residual add + RMSNorm, ONE kernel (llama.rs:398-410):
  *   h = x + residual (model dtype; either may be NULL = absent), residual_out = h (may be NULL, may
  *   alias x or residual), normed = dtype( h * rsqrt(mean(h^2) + eps) * weight ) in fp32 (may be NULL).
@@ -212,10 +223,11 @@ void atoma_debug_skinny_budget(int kib);
  * 4 gate_up -> Wdown, 8 down_proj -> next Wqkv / lm_head, 16 qkv -> Wo; default 0 (measured: no gain).  cap_mib: bytes per edge
  * (default 32; 0 keeps the current value). */
 void atoma_debug_step_prefetch(int mask, int cap_mib);
-/* atoma_llama_decode_step: 1 = the add+RMSNorm after o_proj / down_proj runs in the tail of those GEMMs
+/* atoma_llama_decode_step, bit 1 (value 2): gate_up + SwiGLU and down_proj as two kernels instead of the chained one
+ * (default: chained, 6 launches per layer).  Bit 0: 1 = the add+RMSNorm after o_proj / down_proj runs in the tail of those GEMMs
  * (5 launches per layer, under tensor parallelism the receive side of the all-reduce included); 0 (default) =
  * separate kernels (7 launches per layer; measured 1.5 us per norm faster).  Same bits either way. */
-void atoma_debug_step_fusion(int norm_tail);
+void atoma_debug_step_fusion(int flags);
 
 #ifdef __cplusplus
 }

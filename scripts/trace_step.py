@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--ctx", type=int, default=4096)
     ap.add_argument("--tp", type=int, default=1)
+    ap.add_argument("--fusion", type=int, default=0, help="atoma_debug_step_fusion flags (2 = MLP as two kernels)")
     ap.add_argument("--out", default="gpurun_out/trace_step.json")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -40,6 +41,7 @@ def main():
     tokens, pos, slots = wl.tokens.to(dev), wl.pos.to(dev), wl.slots.to(dev)
     bt, lens = wl.perm.contiguous().to(dev), wl.lens.to(dev)
     ops.set_launch_mode(pdl=True, const_weights=True)
+    L.atoma_debug_step_fusion(args.fusion)
     st = DecodeStep(shard, wl.kv[: args.layers], max_batch=args.batch, no_comm=args.tp > 1, want_hidden=True)
     st.bind(tokens, pos, slots, bt, lens)
     st.launch()                      # library workspaces
@@ -72,7 +74,7 @@ def main():
     for i in idx:
         k = t[i]
         name = labels[i]
-        if name.startswith("gemm"):
+        if name.startswith("gemm") or name.startswith("chain"):
             live = k[:, 3] > 0
             start, end = k[live, 0], k[live, 3]
             first_land, last_land = k[live, 1], k[live, 7]
@@ -98,7 +100,6 @@ def main():
         if dep is not None:
             rec["dependency_resolved"] = us(np.median(dep))
         if first_land is not None:
-            rec["first_issue"] = us(np.median(first_issue))
             rec["first_stage_landed"] = us(np.median(first_land))
             rec["last_stage_landed"] = [us(last_land.min()), us(np.median(last_land)), us(last_land.max())]
         if name.startswith("decode"):
@@ -107,7 +108,7 @@ def main():
             rec["start_minus_prev_end"] = round(rec["first_cta_start"] - prev_end, 2)
         prev_end = rec["end"]
         # SM hand-over: for every SM, this kernel's CTA start minus the end of the previous traced CTA on that SM
-        sm = (k[live, 4] if name.startswith("gemm") else k[live, 0] if name.startswith("decode") else None)
+        sm = (k[live, 4] if name.startswith("gemm") or name == "chain gate_up+silu" else k[live, 0] if name.startswith("decode") else None)
         if sm is not None:
             d = []
             for s_, st_, en_ in zip(sm.tolist(), start.tolist(), end.tolist()):

@@ -303,6 +303,50 @@ def test_gemm_tn_add_rmsnorm_is_bit_identical_to_the_two_calls(T, N, K, dtype):
         ops.set_launch_mode()
 
 
+@pytest.mark.parametrize("T,hidden,inter,dtype", [(32, 4096, 14336, BF), (1, 2048, 8192, BF), (7, 512, 1024, F16), (64, 4096, 1792, BF),
+                                                  (128, 1024, 2048, BF), (100, 8192, 3584, BF)])
+def test_mlp_chain_is_bit_identical_to_the_two_kernels(T, hidden, inter, dtype):
+    """gate_up + SwiGLU and down_proj chained in one kernel (needs programmatic dependent launch) against the two
+    separate kernels: same bits for the activations and the output; its grid-wide arrival counter resets itself
+    (repeated launches, graph replay with two chains back to back)."""
+    x = randn_t((T, hidden), 61, dtype, DEV)
+    wgu = randn_t((2 * inter, hidden), 62, dtype, DEV, scale=hidden ** -0.5)
+    wd = randn_t((hidden, inter), 63, dtype, DEV, scale=inter ** -0.5)
+    ops.reset_launch_count()
+    act0 = ops.gate_up_silu(x, wgu)
+    y0 = ops.gemm_tn(act0, wd)
+    assert ops.launch_count() == 2
+    ops.set_launch_mode(pdl=True, const_weights=True)
+    try:
+        for it in range(3):
+            ops.reset_launch_count()
+            y, act = ops.mlp_gate_up_down(x, wgu, wd)
+            torch.cuda.synchronize()
+            assert ops.launch_count() == 1, "the shapes qualify for the chained kernel"
+            assert torch.equal(act, act0) and torch.equal(y, y0), f"launch {it}"
+        ya, aa = torch.empty_like(y0), torch.empty_like(act0)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            ops.mlp_gate_up_down(x, wgu, wd, act=aa, out=ya)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            ops.mlp_gate_up_down(x, wgu, wd, act=aa, out=ya)
+            ops.mlp_gate_up_down(x, wgu, wd, act=aa, out=ya)
+        for _ in range(3):
+            ya.zero_(); aa.zero_()
+            g.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(aa, act0) and torch.equal(ya, y0)
+    finally:
+        ops.set_launch_mode()
+    # without programmatic dependent launch the same entry runs the two kernels
+    ops.reset_launch_count()
+    y2, act2 = ops.mlp_gate_up_down(x, wgu, wd)
+    assert ops.launch_count() == 2 and torch.equal(y2, y0) and torch.equal(act2, act0)
+
+
 def test_gemm_tn_add_rmsnorm_errors():
     x = randn_t((4, 128), 1, BF, DEV)
     w = randn_t((16392, 128), 2, BF, DEV)
