@@ -17,10 +17,14 @@ the model dtype wherever the reference materialises a tensor in that dtype:
   * tensor parallelism .......... models/src/llama_nccl.rs:97-139, multi_gpu.rs:141-179 (column / row
                                   parallel linears, all-reduce(sum) in the model dtype)
 
-PARITY UNPINNED for the candle-side ops (candle-core / candle-nn / candle-kernels / candle-transformers
-0.9.2-alpha.1 are registry dependencies pinned in Cargo.lock, absent from /root/reference, and the
-reference holds no test that asserts values of RoPE, RMSNorm, SiLU, Linear or the logits): what is
-restated is their published algorithm —
+PARITY for the candle-side ops is UNPINNED BY THE REFERENCE (candle-core / candle-nn / candle-kernels /
+candle-transformers 0.9.2-alpha.1 are registry dependencies pinned in Cargo.lock, absent from /root/reference,
+and the reference holds no test that asserts values of RoPE, RMSNorm, SiLU, Linear or the logits).  Substitute
+anchor: an independent implementation of the same architecture — Hugging Face transformers' Llama in float64,
+of which candle-transformers' llama (what models/src/llama.rs follows) is a port: tests/golden/make_llama_golden.py
+commits its KV caches and logits for four sequences and tests/test_llama_oracle.py reproduces the logits with this
+module's `exact` path to 1e-6 (non-interleaved RoPE with Llama-3 scaling, RMSNorm, GQA attention over a paged
+cache, SwiGLU, residual wiring, final norm, lm_head).  What is restated is the ops' published algorithm —
   rms_norm:  y = T( x * rsqrt(mean(x^2) + eps) * w ), statistics and products in fp32;
   silu:      x / (1 + exp(-x));   rope: see attention_oracle.rope;   Linear: x @ W^T.
 The attention and cache pieces reuse the pinned oracle.  `exact=True` variants skip the intermediate
@@ -77,6 +81,29 @@ def greedy(logits: np.ndarray):
     return idx.astype(np.int64), x[np.arange(x.shape[0]), idx]
 
 
+def _paged_decode_fp64(q, k_cache, v_cache, block_tables, seq_lens, scale):
+    """softmax(scale q K^T) V per sequence and head in float64; K/V rows gathered through the block table
+    (utils.h:305-313), kv head = head // (H / Hkv) (flash_fwd_kernel.h:593), empty sequence -> 0."""
+    q = np.asarray(q, np.float64)
+    T, h, d = q.shape
+    page, hk = k_cache.shape[1], k_cache.shape[2]
+    out = np.zeros((T, h, d), np.float64)
+    for t in range(T):
+        n = int(seq_lens[t])
+        if n <= 0:
+            continue
+        pos = np.arange(n)
+        blk = np.asarray(block_tables[t])[pos // page]
+        k = np.asarray(k_cache, np.float64)[blk, pos % page]      # [n, hk, d]
+        v = np.asarray(v_cache, np.float64)[blk, pos % page]
+        for head in range(h):
+            kvh = head // (h // hk)
+            s_ = (k[:, kvh] @ q[t, head]) * scale
+            p = np.exp(s_ - s_.max())
+            out[t, head] = (p @ v[:, kvh]) / p.sum()
+    return out
+
+
 @dataclass
 class LayerWeights:
     wq: np.ndarray
@@ -127,9 +154,14 @@ def decode_step(hidden: np.ndarray, layers: List[LayerWeights], kv_caches: List[
                 continue
             kc[s // page, s % page] = k[t]
             vc[s // page, s % page] = v[t]
+        if exact:
+            # no model-dtype rounding anywhere, the attention boundary included (ao.attention_paged_decode takes 16-bit
+            # buffers like the FFI does): the same gather + softmax in float64 — pinned against Hugging Face's Llama by
+            # tests/test_llama_oracle.py::test_decode_step_oracle_reproduces_hf_llama_logits
+            return _paged_decode_fp64(q, kc, vc, block_tables, seq_lens, scale).reshape(T, h * D)
         o, _ = ao.attention_paged_decode(q.reshape(T, 1, h, D).astype(np.float32), kc.astype(np.float32),
                                          vc.astype(np.float32), block_tables, seq_lens, scale, is_bf16,
-                                         precision="fp64", exact=exact)
+                                         precision="fp64", exact=False)
         return np.asarray(o, np.float64).reshape(T, h * D)
 
     for l, lw in enumerate(layers):

@@ -138,3 +138,71 @@ def test_rope_tables_follow_cache_new():
     assert low.any()
     j = int(np.argmax(low))
     np.testing.assert_allclose(cs[:, j].numpy(), np.cos(np.arange(32) * inv_p[j] / 8.0), rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# Pin against an independent implementation: Hugging Face transformers' Llama in float64
+# (tests/golden/make_llama_golden.py -> tests/golden/llama_decode_hf.npz)
+# ------------------------------------------------------------------------------------------------
+def _hf_fixture():
+    from pathlib import Path
+    return np.load(Path(__file__).resolve().parent / "golden" / "llama_decode_hf.npz")
+
+
+def test_decode_step_oracle_reproduces_hf_llama_logits():
+    """One decode step of the oracle (exact = fp64, no model-dtype roundings) on the KV cache Hugging Face's Llama
+    built for the first n-1 tokens of each sequence reproduces HF's logits for token n: non-interleaved RoPE with
+    Llama-3 frequency scaling, RMSNorm, GQA attention over the paged cache, SwiGLU MLP, residual wiring, final norm
+    and lm_head — to 1e-6 (HF evaluates the RMSNorm statistics, the softmax and the rotary tables in float32 even in a
+    float64 model; a bf16 rounding anywhere would show as 4e-3).  Sequences of 37, 1, 100 and 64 tokens (a one-token
+    sequence: empty cache)."""
+    fx = _hf_fixture()
+    hid, inter, vocab, L, H, HK, D = [int(v) for v in fx["cfg"]]
+    lens = [int(v) for v in fx["lens"]]
+    T, page = len(lens), 16
+    w = lambda n: np.asarray(fx["w/" + n], np.float64)
+    layers = [lo.LayerWeights(w(f"model.layers.{l}.self_attn.q_proj.weight"), w(f"model.layers.{l}.self_attn.k_proj.weight"),
+                              w(f"model.layers.{l}.self_attn.v_proj.weight"), w(f"model.layers.{l}.self_attn.o_proj.weight"),
+                              w(f"model.layers.{l}.mlp.gate_proj.weight"), w(f"model.layers.{l}.mlp.up_proj.weight"),
+                              w(f"model.layers.{l}.mlp.down_proj.weight"), w(f"model.layers.{l}.input_layernorm.weight"),
+                              w(f"model.layers.{l}.post_attention_layernorm.weight")) for l in range(L)]
+    # paged caches holding HF's K (post-RoPE) and V of every token but the last, blocks in a shuffled order
+    mb = (max(lens) + page - 1) // page
+    nb = T * mb + 3
+    rng = np.random.default_rng(1)
+    bt = rng.permutation(nb)[: T * mb].astype(np.int32).reshape(T, mb)
+    caches = [np.zeros((2, nb, page, HK, D), np.float64) for _ in range(L)]
+    for b, n in enumerate(lens):
+        for l in range(L):
+            k, v = fx[f"k_{b}_{l}"], fx[f"v_{b}_{l}"]            # [Hkv, n, D]
+            for t in range(n - 1):
+                caches[l][0][bt[b, t // page], t % page] = k[:, t]
+                caches[l][1][bt[b, t // page], t % page] = v[:, t]
+    pos = np.asarray(lens) - 1
+    slots = np.asarray([bt[b, p // page] * page + p % page for b, p in enumerate(pos)], np.int64)
+    hidden = np.stack([w("model.embed_tokens.weight")[int(fx[f"tokens_{b}"][-1])] for b in range(T)])
+    _, logits = lo.decode_step(hidden, layers, caches, w("model.norm.weight"), w("lm_head.weight"), fx["rope_cos"], fx["rope_sin"],
+                               pos, slots, bt, np.asarray(lens), H, HK, D, 1e-5, True, exact=True)
+    for b in range(T):
+        want = fx[f"logits_{b}"]
+        err = np.abs(logits[b] - want).max() / np.abs(want).max()
+        assert err < 1e-6, f"sequence {b} (len {lens[b]}): {err:.3e}"
+    # the step also wrote the decoded token's K and V where the slot mapping says — HF's K/V of the last token
+    for b, n in enumerate(lens):
+        for l in range(L):
+            blk, off = bt[b, (n - 1) // page], (n - 1) % page
+            assert np.abs(caches[l][0][blk, off] - fx[f"k_{b}_{l}"][:, n - 1]).max() < 1e-5
+            assert np.abs(caches[l][1][blk, off] - fx[f"v_{b}_{l}"][:, n - 1]).max() < 1e-5
+
+
+def test_rope_tables_with_llama3_scaling_match_hf():
+    """The product's rotary tables (atoma_infer_b200.llama.rope_tables ≙ Cache::new, llama.rs:145-199, Llama-3 frequency
+    scaling) against Hugging Face's LlamaRotaryEmbedding for the same configuration (f32 tables vs f64: 1e-6)."""
+    import torch
+    from atoma_infer_b200.llama import Llama3RopeScaling, LlamaConfig, rope_tables
+    fx = _hf_fixture()
+    cfg = LlamaConfig(hidden_size=64, intermediate_size=160, vocab_size=97, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=2, rope_theta=500000.0, max_position_embeddings=256,
+                      rope_scaling=Llama3RopeScaling(8.0, 1.0, 4.0, 64))
+    cos, sin = rope_tables(cfg, torch.float32, "cpu", max_pos=128)
+    assert np.abs(cos.numpy() - fx["rope_cos"]).max() < 2e-6 and np.abs(sin.numpy() - fx["rope_sin"]).max() < 2e-6
