@@ -135,6 +135,12 @@ __device__ __forceinline__ void l2_prefetch_range(const unsigned char *base, lon
     }
 }
 
+// Publish: every write that happens-before this (the caller's own and, through a preceding CTA / warp barrier, its
+// peers') becomes visible at GPU scope before the counter moves.  Lighter than __threadfence() + atomicAdd
+// (MEMBAR.SC.GPU + L1 invalidate on the publishing side, where nothing is about to be read).
+__device__ __forceinline__ void red_release_gpu_add(uint32_t *p, uint32_t v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

@@ -399,7 +399,6 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
                 mbar_wait(&empty[stage], phase ^ 1);   // passes at once during the first trip round the ring
                 unsigned char *dst = ring + stage * a.stage_bytes;
                 if (is_w && a.trigger_late && n == max(total - a.trigger_late, 0)) pdl_launch_dependents();
-                if (a.trace && is_w && lane == 0 && n == total - 1) a.trace[blockIdx.x * 8 + 5] = sk_timer_ns();
                 if (a.trace && is_w && lane == 0 && n == 0) {
                     unsigned smid;
                     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -516,8 +515,12 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     __syncthreads();
     if (a.trace && tid == 0) a.trace[blockIdx.x * 8 + 3] = sk_timer_ns();
     if (warp == 1) {
+        // Measured (scripts/trace_step.py, slot 5 - slot 3): this fence + release takes 1.1 us + 50 ns per accumulator
+        // column the tile used (2.7 us at 32 columns, 11.5 us at 208) — the fence is where the time goes, and dropping
+        // it only moves the wait into tcgen05.dealloc.  It is the SM hand-over cost after every tensor-memory kernel.
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, a.tmem_cols);
+        if (a.trace && lane == 0) a.trace[blockIdx.x * 8 + 5] = sk_timer_ns();   // tensor memory released
     }
 
     if ((EPI == kEpiPlain || EPI == kEpiPush) && a.norm_tail) {
@@ -740,11 +743,11 @@ gemm_chain2_kernel(const __grid_constant__ CUtensorMap map_w0, const __grid_cons
             tc_fence_after_sync();
             if (a0.trace && tid == 64) a0.trace[b * 8 + 2] = sk_timer_ns();
             epilogue_tile<T, M, kEpiSilu>(a0, er, tmem_base + (static_cast<uint32_t>(quad * 32) << 16), g, p0, warp, lane);
-            // this CTA's slice of the activations is stored: publish it to every CTA's phase-1 x producer
-            __threadfence();
+            // this CTA's slice of the activations is stored: publish it to every CTA's phase-1 x producer (the barrier
+            // orders the four warps' stores before the one release)
             named_bar_sync(2, 128);
             if (tid == 64) {
-                atomicAdd(&c.sync[0], 1u);
+                red_release_gpu_add(&c.sync[0], 1u);
                 if (a0.trace) a0.trace[b * 8 + 3] = sk_timer_ns();
             }
         }

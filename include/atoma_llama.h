@@ -206,7 +206,7 @@ void atoma_llama_decode_step(const atoma_llama_model *model, const atoma_decode_
                              atoma_stream_t stream);
 
 /* Diagnostics for the decode-time GEMM: per-CTA timestamps (globaltimer ns) at device_buf[8*cta..]: {0 start,
- * 1 first stage landed, 2 first accumulator complete, 3 end, 4 the SM id, 5 last weight load issued, 6 x producer's
+ * 1 first stage landed, 2 first accumulator complete, 3 end, 4 the SM id, 5 tensor memory released, 6 x producer's
  * grid dependency resolved, 7 last stage landed}; tile width / k blocks per stage / ring depth overrides
  * (0 = automatic). */
 void atoma_debug_skinny_trace(void *device_buf);

@@ -102,6 +102,9 @@ def main():
         if first_land is not None:
             rec["first_stage_landed"] = us(np.median(first_land))
             rec["last_stage_landed"] = [us(last_land.min()), us(np.median(last_land)), us(last_land.max())]
+            if name.startswith("gemm"):
+                dd = (k[live, 5] - k[live, 3]) / 1e3
+                rec["tmem_dealloc_us"] = [round(float(dd.min()), 2), round(float(np.median(dd)), 2), round(float(dd.max()), 2)]
         if name.startswith("decode"):
             rec["streaming_done"] = [us(stream_done.min()), us(np.median(stream_done)), us(stream_done.max())]
         if prev_end is not None:
