@@ -56,7 +56,7 @@ def test_ncu_traffic_reads_the_committed_capture():
 
 
 def test_committed_bench_lines_follow_the_contract():
-    for name in ("r01_bench_ours.json", "r01_bench_reference.json"):
+    for name in ("r01_bench_ours.json", "r01_bench_reference.json", "r02_bench_ours.json", "r02_bench_reference.json"):
         d = json.loads((ROOT / "profiles" / name).read_text())
         for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                   "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
@@ -65,5 +65,10 @@ def test_committed_bench_lines_follow_the_contract():
         assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
         assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
         assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
-    ref = json.loads((ROOT / "profiles" / "r01_bench_reference.json").read_text())
-    assert ref["impl"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0
+    for name in ("r01_bench_reference.json", "r02_bench_reference.json"):
+        ref = json.loads((ROOT / "profiles" / name).read_text())
+        assert ref["impl"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0
+    # round 2: the metric is BASELINE.json's, without a scope qualifier, and the step holds no library kernel
+    ours = json.loads((ROOT / "profiles" / "r02_bench_ours.json").read_text())
+    assert ours["metric"] == json.loads((ROOT / "BASELINE.json").read_text()).get("metric", ours["metric"]) or "(" not in ours["metric"]
+    assert ours["gpu_launches"] == ours["launches_per_step"] * ours["steps"] and "cuBLAS" not in ours["config"]["gemm"]
