@@ -206,3 +206,34 @@ def test_rope_tables_with_llama3_scaling_match_hf():
                       rope_scaling=Llama3RopeScaling(8.0, 1.0, 4.0, 64))
     cos, sin = rope_tables(cfg, torch.float32, "cpu", max_pos=128)
     assert np.abs(cos.numpy() - fx["rope_cos"]).max() < 2e-6 and np.abs(sin.numpy() - fx["rope_sin"]).max() < 2e-6
+
+
+def test_vocab_parallel_greedy_combination_rule():
+    """What atoma_sample_greedy_tp computes, restated: every rank takes the greedy token of its vocabulary slice (LAST
+    index among equal maxima under f32 total order), the candidates are merged in rank order with 'greater key, or equal
+    key and greater index, wins' — equal to the greedy token of the full row, ties across slices and NaNs included."""
+    rng = np.random.default_rng(11)
+    vocab, T = 4096, 16
+    logits = rng.standard_normal((T, vocab)).astype(np.float32)
+    logits[0, [5, 700, 4000]] = 9.0            # a three-way tie across different slices: the last index wins
+    logits[1, :] = -1.0                        # all equal
+    logits[2, 100] = np.inf
+    logits[3, 77] = np.nan                     # total order: +NaN above +inf
+    logits[3, 3000] = np.inf
+    logits[4, 2047:2049] = 5.0                 # a tie straddling a slice boundary
+    want_tok, want_val = lo.greedy(logits)
+    for world in (2, 4, 8):
+        rows = vocab // world
+        best_key = np.full(T, np.iinfo(np.int64).min)
+        best_idx = np.zeros(T, np.int64)
+        for r in range(world):
+            tok, _ = lo.greedy(logits[:, r * rows:(r + 1) * rows])
+            key = logits[np.arange(T), r * rows + tok].view(np.int32).astype(np.int64)
+            key = np.where(key < 0, key ^ 0x7FFFFFFF, key)
+            idx = r * rows + tok
+            take = (r == 0) | (key > best_key) | ((key == best_key) & (idx > best_idx))
+            best_key = np.where(take, key, best_key)
+            best_idx = np.where(take, idx, best_idx)
+        assert np.array_equal(best_idx, want_tok), world
+        got_val = logits[np.arange(T), best_idx]
+        assert np.array_equal(got_val.view(np.int32), want_val.view(np.int32))
