@@ -536,7 +536,14 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         if (j < 0) return;
         uint32_t *state = reinterpret_cast<uint32_t *>(a.norm.region);
         if (tid == 0) {
-            while (ld_acquire_gpu_u32(&a.tail_sync[0]) < static_cast<uint32_t>(grid)) __nanosleep(64);
+            const unsigned long long t_wait = sk_timer_ns();   // bounded like the chained kernel's wait (sticky word [2])
+            while (ld_acquire_gpu_u32(&a.tail_sync[0]) < static_cast<uint32_t>(grid)) {
+                __nanosleep(64);
+                if (sk_timer_ns() - t_wait > 2000000000ull) {
+                    atomicExch(&a.tail_sync[2], 1u);
+                    break;
+                }
+            }
             if (EPI == kEpiPush) {
                 s_tail_state[0] = *reinterpret_cast<volatile uint32_t *>(&state[0]);
                 s_tail_state[1] = *reinterpret_cast<volatile uint32_t *>(&state[2]);
@@ -655,7 +662,17 @@ gemm_chain2_kernel(const __grid_constant__ CUtensorMap map_w0, const __grid_cons
                 // phase 1 reads what EVERY CTA stored in phase 0: wait for all of them, then order the generic-proxy
                 // stores (made visible by the acquire) before this thread's async-proxy (TMA) reads
                 if (lane == 0) {
-                    while (ld_acquire_gpu_u32(&c.sync[0]) < static_cast<uint32_t>(a0.tiles)) __nanosleep(32);
+                    // bounded: every CTA of this grid is resident (at most one per SM) and none waits for this one, so
+                    // the wait ends within the kernel's own run time; the limit only keeps a fault elsewhere (a CTA that
+                    // trapped) from turning into a hung device — the sticky word sync[2] records it
+                    const unsigned long long t_wait = sk_timer_ns();
+                    while (ld_acquire_gpu_u32(&c.sync[0]) < static_cast<uint32_t>(a0.tiles)) {
+                        __nanosleep(32);
+                        if (sk_timer_ns() - t_wait > 2000000000ull) {
+                            atomicExch(&c.sync[2], 1u);
+                            break;
+                        }
+                    }
                     asm volatile("fence.proxy.async;" ::: "memory");
                     if (atomicAdd(&c.sync[1], 1u) == static_cast<uint32_t>(a1.tiles - 1)) {   // last reader: reset for the next launch
                         c.sync[0] = 0;

@@ -543,6 +543,15 @@ extern "C" void atoma_llama_decode_step(const atoma_llama_model *model, const at
     }
 }
 
+extern "C" int64_t atoma_llama_abi_sizeof(int which) {
+    switch (which) {
+        case 0: return static_cast<int64_t>(sizeof(atoma_llama_layer));
+        case 1: return static_cast<int64_t>(sizeof(atoma_llama_model));
+        case 2: return static_cast<int64_t>(sizeof(atoma_decode_batch));
+        default: return -1;
+    }
+}
+
 extern "C" void atoma_debug_skinny_trace(void *device_buf) { set_skinny_trace(device_buf); }
 extern "C" void atoma_debug_skinny_tuning(int np, int kbs, int stages) { set_skinny_tuning(np, kbs, stages); }
 extern "C" void atoma_debug_skinny_mode(int skip_loads, int w_ops) { set_skinny_debug(skip_loads, w_ops); }

@@ -198,6 +198,9 @@ typedef struct atoma_decode_batch {
     float *next_logits;    /* [T] */
 } atoma_decode_batch;
 
+/* sizeof of the structs above as this library was compiled (0 = atoma_llama_layer, 1 = atoma_llama_model,
+ * 2 = atoma_decode_batch): lets a binding in another language assert its mirror of the layout at start-up. */
+int64_t atoma_llama_abi_sizeof(int which);
 int64_t atoma_llama_decode_scratch_bytes(const atoma_llama_model *model, int64_t num_tokens);
 /* One decode step: embedding -> num_layers x [add+rmsnorm, qkv+rope+cache write, paged decode
  * attention, o_proj (+all-reduce), add+rmsnorm, gate_up+silu, down_proj (+all-reduce)] -> add +

@@ -99,3 +99,13 @@ def test_library_matches_the_source_tree():
     L = _lib.lib()
     assert L.atoma_source_hash().decode() == _lib.source_hash()
     assert L.atoma_version().decode().endswith("src:" + _lib.source_hash())
+
+
+def test_ctypes_struct_mirrors_have_the_library_layout():
+    """include/atoma_llama.h's structs as the library was compiled against the ctypes mirrors in _lib.py (the
+    vocab-parallel fields were appended to atoma_llama_model in round 2: a stale mirror would silently misread)."""
+    lib = _lib.load()
+    assert lib.atoma_llama_abi_sizeof(0) == C.sizeof(_lib.LlamaLayer)
+    assert lib.atoma_llama_abi_sizeof(1) == C.sizeof(_lib.LlamaModel)
+    assert lib.atoma_llama_abi_sizeof(2) == C.sizeof(_lib.DecodeBatch)
+    assert lib.atoma_llama_abi_sizeof(3) == -1
