@@ -87,6 +87,7 @@ def test_sass_is_blackwell_native():
                     per_kernel[name].add(op)
     fam = lambda key: set().union(*[ops for n, ops in per_kernel.items() if key in n])
     assert {"UTMALDG", "UTCHMMA", "LDTM", "UTCBAR"} <= fam("gemm_skinny_kernel"), fam("gemm_skinny_kernel")
+    assert {"UTMALDG", "UTCHMMA", "LDTM", "UTCBAR"} <= fam("gemm_chain2_kernel"), fam("gemm_chain2_kernel")
     assert {"UTMALDG", "UTCHMMA", "LDTM"} <= fam("gemm_tn_stream_kernel")
     assert {"UTMALDG", "UTCHMMA", "LDTM", "STTM"} <= fam("prefill_attn_kernel")
     assert {"UTMALDG", "HMMA"} <= fam("decode_paged_kernel")      # GQA rows cannot fill a 128-row tcgen05 tile
