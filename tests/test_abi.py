@@ -110,3 +110,17 @@ def test_ctypes_struct_mirrors_have_the_library_layout():
     assert lib.atoma_llama_abi_sizeof(1) == C.sizeof(_lib.LlamaModel)
     assert lib.atoma_llama_abi_sizeof(2) == C.sizeof(_lib.DecodeBatch)
     assert lib.atoma_llama_abi_sizeof(3) == -1
+
+
+@pytest.mark.parametrize("header", [h.name for h in HEADERS])
+def test_headers_are_plain_c99(header, tmp_path):
+    """The boundary is a C ABI: every header compiles as C99 on its own (what cgo / bindgen / a C host would see) —
+    no C++ types, no torch types, no missing includes."""
+    import shutil
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text(f'#include "{header}"\nint main(void) {{ return 0; }}\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{ROOT / 'include'}", "-fsyntax-only", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
