@@ -124,3 +124,30 @@ def test_headers_are_plain_c99(header, tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{ROOT / 'include'}", "-fsyntax-only", str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_static_archive_links_with_the_reference_link_line(tmp_path):
+    """csrc/build.rs:104-113 links `static=flashattention`, `dylib=cudart`, `dylib=stdc++` and nothing else: a C program
+    that references symbols of all three headers links against libflashattention.a with exactly those libraries and runs
+    (version / status calls only — no GPU needed)."""
+    import os
+    import shutil
+    cudart = Path("/usr/local/cuda/lib64")
+    if shutil.which("gcc") is None or not (cudart / "libcudart.so").exists():
+        pytest.skip("needs gcc and the CUDA runtime library")
+    src = tmp_path / "link_check.c"
+    src.write_text('#include "atoma_flash.h"\n#include "atoma_llama.h"\n#include "atoma_ops.h"\n#include <stdio.h>\n'
+                   'int main(void) {\n'
+                   '    void *keep[] = {(void *)run_mha, (void *)copy_blocks_bf16, (void *)reshape_and_cache_flash,\n'
+                   '                    (void *)atoma_llama_decode_step, (void *)atoma_prepare_input};\n'
+                   '    printf("%s %lld %d\\n", atoma_version(), (long long)atoma_llama_abi_sizeof(1), (int)(sizeof keep / sizeof keep[0]));\n'
+                   '    return atoma_last_status();\n}\n')
+    exe = tmp_path / "link_check"
+    lib_dir = _lib.LIB_PATH.parent
+    r = subprocess.run(["gcc", "-std=c99", f"-I{ROOT / 'include'}", str(src), f"-L{lib_dir}", "-l:libflashattention.a",
+                        f"-L{cudart}", "-lcudart", "-lstdc++", "-lm", "-ldl", "-lpthread", "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    env = dict(os.environ, LD_LIBRARY_PATH=f"{cudart}:{os.environ.get('LD_LIBRARY_PATH', '')}")
+    out = subprocess.run([str(exe)], capture_output=True, text=True, env=env)
+    assert out.returncode == 0 and "sm_100a" in out.stdout, out.stdout + out.stderr
