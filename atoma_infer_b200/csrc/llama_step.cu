@@ -3,9 +3,9 @@
 // The executor restates, for a decode-only batch, what the reference assembles from candle calls in
 // models/src/llama.rs:253-314 (CausalSelfAttention::forward), :362-366 (Mlp::forward), :398-410
 // (Block::forward), :456-478 (Llama::forward) and, under tensor parallelism, llama_nccl.rs:97-139 +
-// multi_gpu.rs:141-179 — as 7 kernel launches per layer on one stream:
+// multi_gpu.rs:141-179 — as 6 kernel launches per layer on one stream (7 without programmatic dependent launch):
 //   add + RMSNorm | qkv GEMM (+RoPE +cache write) | paged decode attention | o_proj GEMM (+push) |
-//   add + RMSNorm (+all-reduce receive) | gate_up GEMM (+SwiGLU) | down GEMM (+push)
+//   add + RMSNorm (+all-reduce receive) | gate_up GEMM (+SwiGLU) chained with down GEMM (+push)
 // It owns no memory (weights, caches, scratch and outputs are the caller's) and never synchronises,
 // so the caller captures it in a CUDA graph once per batch shape.
 #include "atoma_llama.h"

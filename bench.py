@@ -14,9 +14,9 @@ batch 32, every sequence at context 4096, block_size 16 — the whole model, as 
 with a distinct 541 MB KV cache per layer and 15 GB of weights: 32.2 GB of HBM traffic per step, far
 larger than L2 (no flush needed).  Metric: decode tokens/s = batch / step time, whole job.
 
-`--impl ours`: the product — `atoma_llama_decode_step` (atoma_infer_b200.llama.DecodeStep): 7 hand-written
+`--impl ours`: the product — `atoma_llama_decode_step` (atoma_infer_b200.llama.DecodeStep): 6 hand-written
 sm_100a kernels per layer (fused qkv+RoPE+cache-write GEMM, paged decode attention, o_proj GEMM, fused
-add+RMSNorm x2, fused gate_up+SwiGLU GEMM, down_proj GEMM), no library kernel in the step, replayed from
+add+RMSNorm x2, gate_up+SwiGLU and down_proj chained in one kernel), no library kernel in the step, replayed from
 one CUDA graph; the step's inputs come from `InputStager` (one host-to-device copy per step).
 
 `--impl reference`: the REFERENCE's own kernels (oracle/_ref, compiled from /root/reference/csrc/kernels

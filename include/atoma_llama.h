@@ -204,7 +204,8 @@ int64_t atoma_llama_abi_sizeof(int which);
 int64_t atoma_llama_decode_scratch_bytes(const atoma_llama_model *model, int64_t num_tokens);
 /* One decode step: embedding -> num_layers x [add+rmsnorm, qkv+rope+cache write, paged decode
  * attention, o_proj (+all-reduce), add+rmsnorm, gate_up+silu, down_proj (+all-reduce)] -> add +
- * final norm -> lm_head -> greedy sample: 7 launches per layer, no host synchronisation. */
+ * final norm -> lm_head -> greedy sample: 6 launches per layer with programmatic dependent launch enabled (gate_up and
+ * down_proj share one kernel), 7 without; no host synchronisation. */
 void atoma_llama_decode_step(const atoma_llama_model *model, const atoma_decode_batch *batch,
                              atoma_stream_t stream);
 
