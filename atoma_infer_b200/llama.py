@@ -3,7 +3,7 @@ rotary tables, per-rank weight layout and the decode-step executor.
 
 What the reference assembles per step from candle calls (models/src/llama.rs:253-314, 362-366,
 398-410, 456-478; tensor parallel: llama_nccl.rs:97-139, multi_gpu.rs:8-57, 141-179) is ONE C call
-here, `atoma_llama_decode_step` (csrc/llama_step.cu): 7 kernel launches per layer on one stream, no
+here, `atoma_llama_decode_step` (csrc/llama_step.cu): 6 kernel launches per layer on one stream, no
 host synchronisation, captured once per batch shape in a CUDA graph by `DecodeStep.capture()` and
 replayed after each `InputStager.refresh()` (atoma_infer_b200/worker.py).
 

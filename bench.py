@@ -401,6 +401,30 @@ def ncu_traffic(kernel_substr: str):
     return best
 
 
+def tp_roofline(ms_step: float, hbm_bytes_per_rank: int, peak_hbm_gbs: float, tp: int, payload_bytes: int,
+                all_reduces: int, fused_push: bool, nvlink_gbs: float = 770.0):
+    """north_star: "1/2/4/8-GPU TP scaling reported as fraction of NVLink-bound roofline".  The target time of a
+    tensor-parallel step is the slower of (this rank's HBM bytes / measured HBM peak) and (the bytes that MUST
+    cross NVLink / link bandwidth) — B200_PROFILING.md's rule for a fused compute+collective, with its measured
+    peer-copy figure of 770 GB/s per direction per GPU (900 nominal).  An all-reduce of P bytes over N ranks must
+    move 2 (N-1)/N P out of (and into) every rank (reduce-scatter + all-gather, the bandwidth-optimal schedule);
+    `protocol` is what this repo's one-shot push actually sends: (N-1) P payload bytes in 8-byte {4 data, epoch}
+    units = 2 (N-1) P on the wire — latency-optimal, not bandwidth-optimal, at a 256 KiB payload."""
+    hbm_ms = hbm_bytes_per_rank / (peak_hbm_gbs * 1e9) * 1e3
+    must = all_reduces * 2.0 * (tp - 1) / tp * payload_bytes
+    sent = all_reduces * 2.0 * (tp - 1) * payload_bytes if fused_push else must
+    nv_ms, nv_sent_ms = must / (nvlink_gbs * 1e9) * 1e3, sent / (nvlink_gbs * 1e9) * 1e3
+    target = max(hbm_ms, nv_ms)
+    return {"bound": "hbm" if hbm_ms >= nv_ms else "nvlink", "hbm_ms": hbm_ms, "nvlink_ms": nv_ms,
+            "nvlink_ms_as_sent": nv_sent_ms, "nvlink_bytes_per_rank_per_step": int(must),
+            "nvlink_bytes_per_rank_per_step_as_sent": int(sent), "target_ms": target, "frac": target / ms_step,
+            "frac_serial": (hbm_ms + nv_ms) / ms_step,
+            "nvlink_gbs": nvlink_gbs, "hbm_gbs": peak_hbm_gbs,
+            "note": "target = max(HBM time, NVLink time), i.e. perfect overlap; frac_serial = (HBM + NVLink) / measured, "
+                    "no overlap; peaks: MEASURED_PEAKS.json hbm_gbs and B200_PROFILING.md's measured peer copy "
+                    "(770 GB/s per direction per GPU), both 'of measured'"}
+
+
 def tp_parity(torch, args, cfg, batch, ctx, layers, rank, world, dev, arm, dist):
     """N > 1: the tensor-parallel step's result against a tp=1 recomputation of the SAME step on rank 0
     (full weights and caches rebuilt from the same seeds).  Two numbers: after ONE layer without the head
@@ -734,6 +758,9 @@ def main():
             if t:
                 line["roofline"]["traffic"] = t["bytes"]
                 line["roofline"]["traffic_source"] = t["file"] + " (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, same inputs)"
+        if tp > 1 and not args.emulate_tp:
+            line["tp_roofline"] = tp_roofline(ms_step, step_bytes, peak_hbm, tp, batch * cfg.hidden_size * 2, 2 * layers,
+                                              fused_push=args.impl == "ours")
         if parity is not None:
             line["tp_parity"] = parity
         if args.emulate_tp:

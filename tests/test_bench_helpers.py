@@ -72,3 +72,23 @@ def test_committed_bench_lines_follow_the_contract():
     ours = json.loads((ROOT / "profiles" / "r02_bench_ours.json").read_text())
     assert ours["metric"] == json.loads((ROOT / "BASELINE.json").read_text()).get("metric", ours["metric"]) or "(" not in ours["metric"]
     assert ours["gpu_launches"] == ours["launches_per_step"] * ours["steps"] and "cuBLAS" not in ours["config"]["gemm"]
+
+
+def test_tp_roofline_is_the_slower_of_hbm_and_nvlink():
+    """north_star: TP scaling as a fraction of the NVLink-bound roofline (bench.tp_roofline, added to every N > 1 line)."""
+    payload, ars = 32 * 4096 * 2, 64                      # [B, hidden] bf16, two all-reduces per layer
+    r = bench.tp_roofline(3.0, 4_024_180_736, 6542.4, 8, payload, ars, fused_push=True)
+    assert r["bound"] == "hbm" and abs(r["hbm_ms"] - 0.6151) < 1e-3
+    assert r["nvlink_bytes_per_rank_per_step"] == int(ars * 2 * 7 / 8 * payload)          # reduce-scatter + all-gather
+    assert r["nvlink_bytes_per_rank_per_step_as_sent"] == ars * 2 * 7 * payload           # one-shot push, 8-byte flagged units
+    assert abs(r["frac"] - r["target_ms"] / 3.0) < 1e-12 and r["frac"] < r["frac_serial"] < 1.0
+    # a step that streams almost nothing per rank is bound by the link
+    r = bench.tp_roofline(1.0, 1_000_000, 6542.4, 8, payload, ars, fused_push=False)
+    assert r["bound"] == "nvlink" and r["target_ms"] == r["nvlink_ms"] == r["nvlink_ms_as_sent"]
+    # derived from the committed round-2 lines (measured step times): the strong-scaling curve against this roofline
+    for n in (2, 4, 8):
+        d = json.loads((ROOT / "profiles" / f"r02_bench_tp{n}_ours.json").read_text())
+        c = d["config"]
+        r = bench.tp_roofline(d["ms_per_step"], c["hbm_bytes_per_step_per_rank"], d["roofline"]["peak"], n,
+                              c["batch"] * c["hidden"] * 2, 2 * c["layers"], fused_push=True)
+        assert r["bound"] == "hbm" and abs(r["frac"] - c["step_hbm_roofline_frac"]) < 1e-6
