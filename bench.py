@@ -759,7 +759,7 @@ def main():
                 line["roofline"]["traffic"] = t["bytes"]
                 line["roofline"]["traffic_source"] = t["file"] + " (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, same inputs)"
         if tp > 1 and not args.emulate_tp:
-            line["tp_roofline"] = tp_roofline(ms_step, step_bytes, peak_hbm, tp, batch * cfg.hidden_size * 2, 2 * layers,
+            line["tp_roofline"] = tp_roofline(ms_step_e2e if args.impl == "reference" else ms_step, step_bytes, peak_hbm, tp, batch * cfg.hidden_size * 2, 2 * layers,
                                               fused_push=args.impl == "ours")
         if parity is not None:
             line["tp_parity"] = parity
