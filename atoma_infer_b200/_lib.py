@@ -231,6 +231,7 @@ SIGNATURES = {
     "atoma_debug_step_prefetch": (None, [C.c_int] * 2),
     "atoma_debug_step_fusion": (None, [C.c_int]),
     "atoma_llama_abi_sizeof": (C.c_int64, [C.c_int]),
+    "atoma_llama_step_status": (C.c_int, [C.c_void_p]),
     "atoma_mlp_gate_up_down": (None, [C.c_void_p] * 5 + [C.c_int64] * 8 + [C.c_uint32, C.c_void_p]),
     "atoma_sample_greedy_tp": (None, [C.c_void_p] + [C.c_int64] * 4 + [C.c_uint32, C.c_void_p, C.c_void_p,
                                                                         C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64, C.c_void_p]),

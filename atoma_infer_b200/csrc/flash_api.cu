@@ -10,9 +10,10 @@
 #include <cstdarg>
 #include <atomic>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
-#include <unordered_map>
+#include <tuple>
 #include <vector>
 
 namespace atoma {
@@ -160,14 +161,11 @@ void *get_workspace(cudaStream_t stream, size_t bytes, int tag) {
         size_t size = 0;
     };
     static std::mutex mu;
-    static std::unordered_map<uint64_t, Buf> bufs;
+    static std::map<std::tuple<int, int, cudaStream_t>, Buf> bufs;   // (device, tag, stream handle): exact, no hashing
     int dev = 0;
     cudaGetDevice(&dev);
-    // key: device, tag, stream handle
-    const uint64_t key = (reinterpret_cast<uint64_t>(stream) * 1315423911ull) ^
-                         (static_cast<uint64_t>(dev) << 8) ^ static_cast<uint64_t>(tag);
     std::lock_guard<std::mutex> lock(mu);
-    Buf &b = bufs[key];
+    Buf &b = bufs[std::make_tuple(dev, tag, stream)];
     if (b.size >= bytes) return b.ptr;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(stream, &cap);

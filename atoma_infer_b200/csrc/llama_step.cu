@@ -511,7 +511,6 @@ extern "C" void atoma_llama_decode_step(const atoma_llama_model *model, const at
             } else {
                 if (!gemm_tn(s.act, ly.w_down, s.proj, T, hid, m.inter, m.inter, m.inter, hid, dt, stream)) return;
             }
-    
         }
     }
     // x = mlp + residual; ln_f  (llama.rs:408, 474)
@@ -541,6 +540,36 @@ extern "C" void atoma_llama_decode_step(const atoma_llama_model *model, const at
         uint32_t *tok = b.next_tokens ? b.next_tokens : reinterpret_cast<uint32_t *>(s.act);
         launch_argmax(logits, T, m.vocab, m.vocab, dt, tok, b.next_logits, b.logits_f32, m.vocab, stream);
     }
+}
+
+// The in-kernel grid barriers of the step (the chained MLP's "every CTA has stored its activations" counter, the
+// fused norm tail's "every CTA has finished" counter) are bounded: a wait that outlives 2 s — a CTA of the grid
+// trapped, or two grids with such a barrier were forced to share the device and neither became fully resident —
+// gives up, lets the kernel finish with an unusable result and sets a sticky word in the stream's barrier
+// workspace.  This reads those words back (synchronises the stream): bit 0 = fused norm tail, bit 1 = chained MLP.
+extern "C" int atoma_llama_step_status(atoma_stream_t stream_) {
+    clear_status();
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cap);
+    if (cap != cudaStreamCaptureStatusNone) {
+        set_status(kErrUnsupported, "atoma_llama_step_status synchronises the stream: not during capture");
+        return -1;
+    }
+    const uint32_t *ws = static_cast<const uint32_t *>(get_workspace(stream, 256, kWorkspaceSkinnyTail));
+    if (!ws) return -1;
+    uint32_t w[16] = {0};
+    cudaError_t e = cudaMemcpyAsync(w, ws, sizeof(w), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+        set_status(static_cast<int>(e), "atoma_llama_step_status: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    const int bits = (w[2] ? 1 : 0) | (w[10] ? 2 : 0);   // tail_sync[2]; the chain's sync = words 8.. -> sync[2] = word 10
+    if (bits)
+        set_status(kErrUnsupported, "a grid barrier inside a decode-step GEMM timed out (%s%s): the step's results since then are unusable",
+                   (bits & 1) ? "fused norm tail" : "", (bits & 2) ? ((bits & 1) ? ", chained MLP" : "chained MLP") : "");
+    return bits;
 }
 
 extern "C" int64_t atoma_llama_abi_sizeof(int which) {

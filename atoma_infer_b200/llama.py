@@ -328,5 +328,23 @@ class DecodeStep:
         self.launch()
         return int(L.atoma_launch_count())
 
+    def check(self) -> None:
+        """Synchronises the stream the step runs on and raises if a bounded in-kernel wait ever expired on it
+        (`atoma_llama_step_status`: the chained MLP's grid barrier, the fused norm tail) or, under tensor
+        parallelism, if a peer failed to arrive at an all-reduce.  Call it where the serving loop already
+        synchronises (after copying the sampled tokens back)."""
+        L = _lib.lib()
+        cur = torch.cuda.current_stream(self.device)
+        cur.synchronize()                                  # replays run on the current stream ...
+        streams = {cur.cuda_stream}
+        if self._graph_stream is not None:
+            streams.add(self._graph_stream.cuda_stream)    # ... over the barrier workspace of the stream they were captured on
+        for s in streams:
+            rc = L.atoma_llama_step_status(s)
+            if rc != 0:
+                raise AtomaError(L.atoma_last_error().decode() or f"atoma_llama_step_status = {rc}")
+        if self.p2p is not None:
+            self.p2p.check()
+
     def release(self) -> None:
         self._graph = None

@@ -614,6 +614,8 @@ def main():
     ms_e2e = max(e2.elapsed_time(e3), t_e2e_wall * 1e3)  # host wall-clock includes the syncs
     clocks = sampler.stop(t_clock0, time.time()) if sampler else None
     mark("timed region 2 done")
+    if args.impl == "ours":
+        arm.step.check()   # loud if a bounded in-kernel wait (grid barrier, all-reduce peer) ever expired during the runs
 
     # ---- dominant kernel alone: paged decode attention, one launch per layer (distinct caches) ----
     sh = wl.shard.shard

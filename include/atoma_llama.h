@@ -209,6 +209,14 @@ int64_t atoma_llama_decode_scratch_bytes(const atoma_llama_model *model, int64_t
 void atoma_llama_decode_step(const atoma_llama_model *model, const atoma_decode_batch *batch,
                              atoma_stream_t stream);
 
+/* Health of the step's in-kernel grid barriers on `stream` (synchronises it; not during capture).  The chained MLP
+ * kernel and the fused norm tail wait inside the kernel for every CTA of their own grid; the wait is bounded (2 s): if
+ * it ever expires — a CTA trapped, or another grid with such a barrier was running on the same device at the same
+ * time and neither became fully resident — the kernel finishes with an unusable result and sets a sticky word.
+ * Returns 0 = healthy, bit 0 = fused norm tail timed out, bit 1 = chained MLP timed out (atoma_last_error() says so),
+ * -1 = the query itself failed.  Serving loops call it where they already synchronise (the sampled-token copy). */
+int atoma_llama_step_status(atoma_stream_t stream);
+
 /* Diagnostics for the decode-time GEMM: per-CTA timestamps (globaltimer ns) at device_buf[8*cta..]: {0 start,
  * 1 first stage landed, 2 first accumulator complete, 3 end, 4 the SM id, 5 tensor memory released, 6 x producer's
  * grid dependency resolved, 7 last stage landed}; tile width / k blocks per stage / ring depth overrides

@@ -339,6 +339,9 @@ def test_mlp_chain_is_bit_identical_to_the_two_kernels(T, hidden, inter, dtype):
             g.replay()
             torch.cuda.synchronize()
             assert torch.equal(aa, act0) and torch.equal(ya, y0)
+        # the bounded grid barrier never expired on either stream (the sticky words of atoma_llama_step_status)
+        for st in (torch.cuda.current_stream(), side):
+            assert _lib.lib().atoma_llama_step_status(st.cuda_stream) == 0
     finally:
         ops.set_launch_mode()
     # without programmatic dependent launch the same entry runs the two kernels
@@ -507,6 +510,7 @@ def test_decode_step_graph_replay_follows_refreshed_inputs():
             tokens.copy_(tok2); pos.copy_(pos2); slots.copy_(slots2); lens.copy_(lens2)   # in place: same addresses
             step.run()
             torch.cuda.synchronize()
+            step.check()   # no bounded in-kernel wait expired (atoma_llama_step_status on the capture and current streams)
             results.append((first, step.logits[:T].clone(), step.next_tokens[:T].clone(), [c.clone() for c in kv]))
         finally:
             ops.set_launch_mode()
