@@ -41,7 +41,6 @@ class P2PComm:
         self.rank, self.world, self.device, self.slot_bytes = rank, world, device, slot_bytes
         self._local = local
         self._regions = regions                      # ctypes array of world void*
-        self._last_slot = None
 
     @classmethod
     def from_torch_distributed(cls, device, slot_bytes: int) -> "P2PComm":

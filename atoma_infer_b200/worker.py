@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass
-from typing import List, Optional, Sequence as Seq_
+from typing import Optional, Sequence as Seq_
 
 import numpy as np
 import torch

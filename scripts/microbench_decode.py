@@ -3,7 +3,6 @@ ours vs the reference kernels (oracle/_ref), CUDA events, L2 defeated by rotatin
 import json
 import os
 import sys
-import time
 from pathlib import Path
 
 import numpy as np
