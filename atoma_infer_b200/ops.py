@@ -289,10 +289,14 @@ def swap_blocks(src: torch.Tensor, dst: torch.Tensor, block_mapping: Dict[int, i
 
 def gemm_bf16_tn(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y[T, N] = x[T, K] @ w[N, K]^T (bf16, fp32 accumulate): models/src/llama.rs:269-271, 311"""
+    _mat("x", x, dtype=torch.bfloat16)
     T, K = x.shape
+    _mat("w", w, cols=K, dtype=torch.bfloat16)
     N = w.shape[0]
     if out is None:
         out = torch.empty((T, N), dtype=x.dtype, device=x.device)
+    _mat("out", out, T, N, x.dtype)
+    _cuda(x=x, w=w, out=out)
     L = _lib.lib()
     L.atoma_gemm_bf16_tn(x.data_ptr(), w.data_ptr(), out.data_ptr(), T, N, K, x.stride(0), w.stride(0),
                          out.stride(0), _stream())
@@ -344,6 +348,31 @@ def _dt(t: torch.Tensor) -> int:
     return 1 if t.dtype == torch.bfloat16 else 0
 
 
+def _mat(name: str, t: torch.Tensor, rows: Optional[int] = None, cols: Optional[int] = None,
+         dtype: Optional[torch.dtype] = None) -> None:
+    """What every matrix argument of the decode-step operators must be — the C entries take a pointer and a ROW
+    stride only, so a transposed or otherwise non-row-major view or a mismatched dtype would be read as something
+    else without any error: refuse them here (candle's `Linear::forward` makes its operands contiguous
+    instead; a silent copy is not this library's to make)."""
+    if t.dim() != 2:
+        raise AtomaError(f"{name} must be a 2-D tensor, got shape {tuple(t.shape)}")
+    if (rows is not None and t.shape[0] != rows) or (cols is not None and t.shape[1] != cols):
+        want = f"[{rows if rows is not None else '*'}, {cols if cols is not None else '*'}]"
+        raise AtomaError(f"{name} must be {want}, got {tuple(t.shape)}")
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        raise AtomaError(f"{name} must be row-major (element stride 1 in its last dimension, got {t.stride(1)}): "
+                         "pass .contiguous() of a transposed view")
+    if dtype is not None and t.dtype != dtype:
+        raise AtomaError(f"{name} must have dtype {dtype}, got {t.dtype}")
+
+
+def _cuda(**named) -> None:
+    """Last check of a wrapper (after shapes, layouts and dtypes): every tensor handed to a kernel lives on a GPU."""
+    for name, t in named.items():
+        if t is not None and not t.is_cuda:
+            raise AtomaError(f"{name} must be a CUDA tensor (there is no CPU path)")
+
+
 def _raise_on_status() -> None:
     L = _lib.lib()
     if L.atoma_last_status() != 0:
@@ -352,10 +381,14 @@ def _raise_on_status() -> None:
 
 def gemm_tn(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y[T, N] = x[T, K] @ w[N, K]^T for f16/bf16 (`Linear::forward`, llama.rs:269-271, 311, 365, 476)."""
+    _mat("x", x)
     T, K = x.shape
+    _mat("w", w, cols=K, dtype=x.dtype)
     N = w.shape[0]
     if out is None:
         out = torch.empty((T, N), dtype=x.dtype, device=x.device)
+    _mat("out", out, T, N, x.dtype)
+    _cuda(x=x, w=w, out=out)
     _lib.lib().atoma_gemm_tn(x.data_ptr(), w.data_ptr(), out.data_ptr(), T, N, K, x.stride(0), w.stride(0),
                              out.stride(0), _dt(x), _stream())
     _raise_on_status()
@@ -366,16 +399,21 @@ def qkv_rope_cache(x, wqkv, num_heads: int, num_kv_heads: int, head_size: int, p
                    key_cache=None, value_cache=None, slot_mapping=None, out=None) -> torch.Tensor:
     """Fused q/k/v projection + RoPE + KV-cache write (llama.rs:269-304 + flash_attention.rs:361) ->
     qkv [T, (H + 2 Hkv) D] with q and k rotated."""
+    _mat("x", x)
     T, K = x.shape
     N = (num_heads + 2 * num_kv_heads) * head_size
-    if wqkv.shape[0] != N or wqkv.shape[1] != K:
+    if wqkv.dim() != 2 or wqkv.shape[0] != N or wqkv.shape[1] != K:
         raise AtomaError(f"wqkv must be [{N}, {K}], got {tuple(wqkv.shape)}")
+    _mat("wqkv", wqkv, N, K, x.dtype)
     if positions.dtype != torch.int64 or positions.numel() != T:
         raise AtomaError(f"input_positions must be of dtype i64 and hold {T} positions")
     if cos.dtype != x.dtype or sin.dtype != x.dtype or cos.shape[-1] != head_size // 2 or sin.shape != cos.shape:
         raise AtomaError(f"cos/sin must be [max_pos, {head_size // 2}] tensors of the activation dtype")
     if out is None:
         out = torch.empty((T, N), dtype=x.dtype, device=x.device)
+    _mat("out", out, T, N, x.dtype)
+    _cuda(x=x, wqkv=wqkv, out=out, input_positions=positions, cos=cos, sin=sin, key_cache=key_cache, value_cache=value_cache,
+          slot_mapping=slot_mapping)
     kc = vc = sm = None
     block_stride = block_size = 0
     if slot_mapping is not None and key_cache is not None:
@@ -397,10 +435,16 @@ def qkv_rope_cache(x, wqkv, num_heads: int, num_kv_heads: int, head_size: int, p
 
 def gate_up_silu(x, w_gate_up, out=None) -> torch.Tensor:
     """silu(x Wg^T) * (x Wu^T) with w_gate_up = cat([Wg, Wu]) (llama.rs:364)."""
+    _mat("x", x)
     T, K = x.shape
+    _mat("w_gate_up", w_gate_up, cols=K, dtype=x.dtype)
+    if w_gate_up.shape[0] % 2:
+        raise AtomaError(f"w_gate_up must stack W_gate on W_up: an even number of rows, got {w_gate_up.shape[0]}")
     inter = w_gate_up.shape[0] // 2
     if out is None:
         out = torch.empty((T, inter), dtype=x.dtype, device=x.device)
+    _mat("out", out, T, inter, x.dtype)
+    _cuda(x=x, w_gate_up=w_gate_up, out=out)
     _lib.lib().atoma_gate_up_silu(x.data_ptr(), w_gate_up.data_ptr(), out.data_ptr(), T, inter, K, x.stride(0),
                                   w_gate_up.stride(0), out.stride(0), _dt(x), _stream())
     _raise_on_status()
@@ -425,12 +469,20 @@ def add_rmsnorm(x, residual, weight, eps: float, residual_out=None, normed=None)
 
 def mlp_gate_up_down(x, w_gate_up, w_down, act=None, out=None):
     """`Mlp::forward` (llama.rs:362-366): down(silu(gate(x)) * up(x)) -> (y, act); one kernel when it qualifies."""
+    _mat("x", x)
     T, hidden = x.shape
+    _mat("w_gate_up", w_gate_up, cols=hidden, dtype=x.dtype)
+    if w_gate_up.shape[0] % 2:
+        raise AtomaError(f"w_gate_up must stack W_gate on W_up: an even number of rows, got {w_gate_up.shape[0]}")
     inter = w_gate_up.shape[0] // 2
+    _mat("w_down", w_down, hidden, inter, x.dtype)
     if act is None:
         act = torch.empty((T, inter), dtype=x.dtype, device=x.device)
     if out is None:
         out = torch.empty((T, w_down.shape[0]), dtype=x.dtype, device=x.device)
+    _mat("act", act, T, inter, x.dtype)
+    _mat("out", out, T, hidden, x.dtype)
+    _cuda(x=x, w_gate_up=w_gate_up, w_down=w_down, act=act, out=out)
     _lib.lib().atoma_mlp_gate_up_down(x.data_ptr(), w_gate_up.data_ptr(), act.data_ptr(), w_down.data_ptr(), out.data_ptr(), T, inter,
                                       hidden, x.stride(0), w_gate_up.stride(0), act.stride(0), w_down.stride(0), out.stride(0),
                                       _dt(x), _stream())
@@ -441,12 +493,18 @@ def mlp_gate_up_down(x, w_gate_up, w_down, act=None, out=None):
 def gemm_tn_add_rmsnorm(x, w, residual, weight, eps: float, out=None, residual_out=None, normed=None):
     """y = x w^T; h = y + residual; normed = rmsnorm(h) * weight — one kernel (llama.rs:311 + 401-407).  Returns
     (y, h, normed); bit-identical to gemm_tn followed by add_rmsnorm."""
+    _mat("x", x)
     T, K = x.shape
+    _mat("w", w, cols=K, dtype=x.dtype)
     N = w.shape[0]
     if out is None:
         out = torch.empty((T, N), dtype=x.dtype, device=x.device)
     if residual_out is None:
         residual_out = torch.empty((T, N), dtype=x.dtype, device=x.device)
+    for name, t in (("out", out), ("residual", residual), ("residual_out", residual_out), ("normed", normed)):
+        if t is not None:
+            _mat(name, t, T, N, x.dtype)
+    _cuda(x=x, w=w, out=out, residual=residual, residual_out=residual_out, weight=weight, normed=normed)
     if normed is None and weight is not None:
         normed = torch.empty((T, N), dtype=x.dtype, device=x.device)
     p = lambda t: t.data_ptr() if t is not None else None
@@ -463,9 +521,14 @@ def embedding(tokens, table, out=None) -> torch.Tensor:
     T = tokens.numel()
     if tokens.dtype not in (torch.int32, getattr(torch, "uint32", torch.int32)):
         raise AtomaError("token ids must be u32")
+    _mat("table", table)
     vocab, hidden = table.shape
+    if not tokens.is_contiguous():
+        raise AtomaError("token ids must be a contiguous tensor")
     if out is None:
         out = torch.empty((T, hidden), dtype=table.dtype, device=table.device)
+    _mat("out", out, T, hidden, table.dtype)
+    _cuda(token_ids=tokens, table=table, out=out)
     _lib.lib().atoma_embedding(tokens.data_ptr(), table.data_ptr(), out.data_ptr(), T, hidden, vocab, table.stride(0),
                                out.stride(0), _dt(table), _stream())
     _raise_on_status()
@@ -474,6 +537,8 @@ def embedding(tokens, table, out=None) -> torch.Tensor:
 
 def sample_greedy(logits, want_f32: bool = False):
     """(token ids int32 [T], their logits f32 [T], optional f32 copy of the logits) — model_executor.rs:227-262."""
+    _mat("logits", logits)
+    _cuda(logits=logits)
     T, vocab = logits.shape
     tok = torch.empty((T,), dtype=torch.int32, device=logits.device)
     val = torch.empty((T,), dtype=torch.float32, device=logits.device)
