@@ -162,3 +162,20 @@ def test_refresh_never_reallocates_the_staging_image():
     assert st.generation == gen
     mi2 = st.prepare_input_tensors(big)          # allowed to grow: hands out fresh views
     assert st.generation == gen + 1 and mi2.attention_metadata.decoding_metadata.block_tables.shape == (8, 400)
+
+
+def test_random_sweep_against_the_restated_reference():
+    """300 random schedules over block sizes, sliding windows (smaller and larger than a block, than the prompts),
+    chunked prefill on / off, prefill-only / decode-only / mixed batches: every tensor and scalar of the packed
+    buffer equals the step-by-step restatement of worker.rs:224-460."""
+    rng = np.random.default_rng(2024)
+    for trial in range(300):
+        block_size = int(rng.choice([1, 4, 8, 16, 32]))
+        window = [None, 1, 5, 8, 24, 64][int(rng.integers(0, 6))]
+        chunked = bool(rng.integers(0, 2))
+        n_prompt, n_decode = int(rng.integers(0, 4)), int(rng.integers(0, 6))
+        if n_prompt + n_decode == 0:
+            n_decode = 1
+        so, sp = _mk(rng, n_prompt, n_decode, block_size, chunked, max_len=int(rng.choice([2, 9, 70, 300])))
+        st = worker.InputStager(None, block_size, window, chunked)
+        _check(st.prepare_input_tensors(sp), orc.prepare_input_tensors(so, block_size, window, chunked))
